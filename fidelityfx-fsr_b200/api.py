@@ -1,0 +1,132 @@
+"""Thin Python layer over the C ABI: torch tensors are used ONLY as device memory + stream handles.
+
+Images are torch CUDA tensors of shape [rows, width, 4], dtype float16 (RGBA16F) or float32 (RGBA32F),
+contiguous in the last two dimensions (the row stride may be padded).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_RCAS_CLAMP, FORMAT_RGBA16F,  # noqa: F401
+                   FORMAT_RGBA32F, Fsr1Error, Image)
+
+
+def _u32(n):
+    return (ctypes.c_uint32 * n)()
+
+
+def easu_con(in_viewport_w, in_viewport_h, in_size_w, in_size_h, out_w, out_h):
+    """FsrEasuCon (reference ffx-fsr/ffx_fsr1.h:156-202): returns the 16 constant words con0..con3."""
+    con = _u32(16)
+    f = ctypes.c_float
+    _lib.lib().fsr1_easu_con(con, f(in_viewport_w), f(in_viewport_h), f(in_size_w), f(in_size_h), f(out_w), f(out_h))
+    return list(con)
+
+
+def easu_con_offset(in_viewport_w, in_viewport_h, in_size_w, in_size_h, out_w, out_h, off_x, off_y):
+    """FsrEasuConOffset (reference ffx-fsr/ffx_fsr1.h:205-225)."""
+    con = _u32(16)
+    f = ctypes.c_float
+    _lib.lib().fsr1_easu_con_offset(con, f(in_viewport_w), f(in_viewport_h), f(in_size_w), f(in_size_h), f(out_w),
+                                    f(out_h), f(off_x), f(off_y))
+    return list(con)
+
+
+def rcas_con(sharpness_stops):
+    """FsrRcasCon (reference ffx-fsr/ffx_fsr1.h:662-672): returns the 4 constant words."""
+    con = _u32(4)
+    _lib.lib().fsr1_rcas_con(con, ctypes.c_float(sharpness_stops))
+    return list(con)
+
+
+def easu_input_rows(con, in_height, y0, y1):
+    a, b = ctypes.c_uint32(), ctypes.c_uint32()
+    _lib.check(_lib.lib().fsr1_easu_input_rows((ctypes.c_uint32 * 16)(*con), in_height, y0, y1, ctypes.byref(a),
+                                               ctypes.byref(b)))
+    return a.value, b.value
+
+
+def image(t, height=None, row0=0):
+    """Describe tensor `t` ([rows, W, 4]) as logical rows [row0, row0+rows) of an image `height` rows tall."""
+    if not t.is_cuda:
+        raise Fsr1Error("fsr1 kernels run on CUDA tensors only (no CPU path)")
+    if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
+        raise Fsr1Error("image tensors must be [rows, width, 4] with contiguous pixels")
+    fmt = {torch.float16: FORMAT_RGBA16F, torch.float32: FORMAT_RGBA32F}.get(t.dtype)
+    if fmt is None:
+        raise Fsr1Error("unsupported dtype %s" % t.dtype)
+    rows, w = int(t.shape[0]), int(t.shape[1])
+    return Image(t.data_ptr(), t.stride(0) * t.element_size(), w, int(height if height is not None else rows), row0,
+                 rows, fmt, 0)
+
+
+def _stream(stream):
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+def _as_img(x):
+    return x if isinstance(x, Image) else image(x)
+
+
+def easu(inp, out, con, y0=0, y1=0, flags=0, stream=None):
+    """EASU over output rows [y0,y1) — the shader dispatch FsrEasuF/H (ffx_fsr1.h:315-437,505-593)."""
+    a, b = _as_img(inp), _as_img(out)
+    _lib.check(_lib.lib().fsr1_easu(ctypes.byref(a), ctypes.byref(b), (ctypes.c_uint32 * 16)(*con), y0, y1, flags,
+                                    _stream(stream)))
+
+
+def rcas(inp, out, con, y0=0, y1=0, flags=0, stream=None):
+    """RCAS over rows [y0,y1) — FsrRcasF/H (ffx_fsr1.h:684-769,782-866)."""
+    a, b = _as_img(inp), _as_img(out)
+    _lib.check(_lib.lib().fsr1_rcas(ctypes.byref(a), ctypes.byref(b), (ctypes.c_uint32 * 4)(*con), y0, y1, flags,
+                                    _stream(stream)))
+
+
+def upscale(inp, tmp, out, econ, rcon, y0=0, y1=0, flags=0, stream=None):
+    """EASU -> RCAS, the body of FSR_Filter::Upscale (sample/src/DX12/FSR_Filter.cpp:101-141)."""
+    a, t, b = _as_img(inp), _as_img(tmp), _as_img(out)
+    _lib.check(_lib.lib().fsr1_upscale(ctypes.byref(a), ctypes.byref(t), ctypes.byref(b), (ctypes.c_uint32 * 16)(*econ),
+                                       (ctypes.c_uint32 * 4)(*rcon), y0, y1, flags, _stream(stream)))
+
+
+def last_kernel():
+    return _lib.lib().fsr1_last_kernel_name().decode()
+
+
+def launch_count():
+    return int(_lib.lib().fsr1_launch_count())
+
+
+class HostContext:
+    """fsr1_context_*: owns the intermediate and device staging; frames live in (pinned) host memory."""
+
+    def __init__(self, in_w, in_h, out_w, out_h, fmt=FORMAT_RGBA16F):
+        self._h = ctypes.c_void_p()
+        self.shape = (in_w, in_h, out_w, out_h)
+        _lib.check(_lib.lib().fsr1_context_create(ctypes.byref(self._h), in_w, in_h, out_w, out_h, fmt))
+
+    def upscale_host(self, in_host, out_host, sharpness=0.25, flags=0, stream=None):
+        _lib.check(_lib.lib().fsr1_context_upscale_host(
+            self._h, ctypes.c_void_p(in_host.data_ptr()), in_host.stride(0) * in_host.element_size(),
+            ctypes.c_void_p(out_host.data_ptr()), out_host.stride(0) * out_host.element_size(),
+            ctypes.c_float(sharpness), flags, _stream(stream)))
+
+    def upscale(self, in_dev, out_dev, sharpness=0.25, flags=0, stream=None):
+        _lib.check(_lib.lib().fsr1_context_upscale(
+            self._h, ctypes.c_void_p(in_dev.data_ptr()), in_dev.stride(0) * in_dev.element_size(),
+            ctypes.c_void_p(out_dev.data_ptr()), out_dev.stride(0) * out_dev.element_size(),
+            ctypes.c_float(sharpness), flags, _stream(stream)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().fsr1_context_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

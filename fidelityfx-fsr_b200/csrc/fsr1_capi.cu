@@ -1,0 +1,255 @@
+// fsr1_capi.cu — the C ABI declared in include/fsr1_b200.h: argument validation, kernel selection,
+// the resource-owning context, and the constant-setup entry points.
+#include <atomic>
+#include <math.h>
+#include <new>
+#include <string.h>
+
+#include "../../include/fsr1_b200.h"
+#include "../../include/fsr1_host.h"
+#include "fsr1_common.cuh"
+
+using namespace fsr1;
+
+namespace {
+
+thread_local int t_last_cuda = 0;
+thread_local const char* t_last_kernel = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int cuda_fail(cudaError_t e) {
+  t_last_cuda = (int)e;
+  return FSR1_ERR_CUDA;
+}
+
+int bytes_per_pixel(uint32_t fmt) { return fmt == FSR1_FORMAT_RGBA16F ? 8 : (fmt == FSR1_FORMAT_RGBA32F ? 16 : 0); }
+
+int check_image(const fsr1_image* im) {
+  if (!im || !im->data || im->width == 0 || im->height == 0 || im->rows == 0) return FSR1_ERR_INVALID_ARGUMENT;
+  const int bpp = bytes_per_pixel(im->format);
+  if (!bpp) return FSR1_ERR_INVALID_ARGUMENT;
+  if (im->width > 32768u || im->height > 32768u) return FSR1_ERR_INVALID_ARGUMENT;
+  if (im->pitch_bytes < (uint64_t)im->width * bpp || (im->pitch_bytes % (bpp == 8 ? 8 : 16)) != 0) return FSR1_ERR_INVALID_ARGUMENT;
+  if ((uintptr_t)im->data % (bpp == 8 ? 8 : 16) != 0) return FSR1_ERR_INVALID_ARGUMENT;
+  if ((uint64_t)im->row0 + im->rows > im->height) return FSR1_ERR_INVALID_ARGUMENT;
+  return FSR1_OK;
+}
+
+ImgView view_of(const fsr1_image* im) {
+  ImgView v;
+  v.base = static_cast<unsigned char*>(im->data);
+  v.pitch = (long long)im->pitch_bytes;
+  v.w = (int)im->width;
+  v.h = (int)im->height;
+  v.row0 = (int)im->row0;
+  v.rows = (int)im->rows;
+  return v;
+}
+
+// identical float arithmetic to easu_pos() on the device and to the oracle
+int host_cell(uint32_t o, float scale, float offset) {
+  volatile float m = (float)o * scale;
+  volatile float s = m + offset;
+  return (int)floorf(s);
+}
+
+float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+bool window_holds(const fsr1_image* im, int first, int last) {  // logical rows [first,last]
+  return first >= (int)im->row0 && last < (int)(im->row0 + im->rows);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fsr1_abi_version(void) { return FSR1_ABI_VERSION; }
+
+const char* fsr1_error_string(int err) {
+  switch (err) {
+    case FSR1_OK: return "ok";
+    case FSR1_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case FSR1_ERR_UNSUPPORTED: return "unsupported format combination";
+    case FSR1_ERR_WINDOW: return "image window does not hold the rows this pass touches";
+    case FSR1_ERR_CUDA: return "CUDA error (see fsr1_last_cuda_error)";
+    case FSR1_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown fsr1 error";
+  }
+}
+int fsr1_last_cuda_error(void) { return t_last_cuda; }
+uint64_t fsr1_launch_count(void) { return g_launches.load(); }
+const char* fsr1_last_kernel_name(void) { return t_last_kernel; }
+
+void fsr1_easu_con(uint32_t con[16], float vw, float vh, float sw, float sh, float ow, float oh) {
+  FsrEasuCon(con, con + 4, con + 8, con + 12, vw, vh, sw, sh, ow, oh);
+}
+void fsr1_easu_con_offset(uint32_t con[16], float vw, float vh, float sw, float sh, float ow, float oh, float ox,
+                          float oy) {
+  FsrEasuConOffset(con, con + 4, con + 8, con + 12, vw, vh, sw, sh, ow, oh, ox, oy);
+}
+void fsr1_rcas_con(uint32_t con[4], float sharpness_stops) { FsrRcasCon(con, sharpness_stops); }
+
+int fsr1_easu_input_rows(const uint32_t con[16], uint32_t in_height, uint32_t y0, uint32_t y1, uint32_t* first_row,
+                         uint32_t* last_row) {
+  if (!con || !first_row || !last_row || in_height == 0 || y1 <= y0) return FSR1_ERR_INVALID_ARGUMENT;
+  const float sy = as_float(con[1]), oy = as_float(con[3]);
+  int lo = host_cell(y0, sy, oy) - 1, hi = host_cell(y1 - 1, sy, oy) + 2;
+  const int H = (int)in_height;
+  lo = lo < 0 ? 0 : (lo > H - 1 ? H - 1 : lo);
+  hi = hi < 0 ? 0 : (hi > H - 1 ? H - 1 : hi);
+  *first_row = (uint32_t)lo;
+  *last_row = (uint32_t)hi;
+  return FSR1_OK;
+}
+
+int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16], uint32_t y0, uint32_t y1,
+              uint32_t flags, void* stream) {
+  int rc;
+  if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
+  if (!con) return FSR1_ERR_INVALID_ARGUMENT;
+  if (in->format != out->format) return FSR1_ERR_UNSUPPORTED;
+  if (y1 == 0) y1 = out->height;
+  if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!window_holds(out, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
+  uint32_t r0, r1;
+  fsr1_easu_input_rows(con, in->height, y0, y1, &r0, &r1);
+  if (!window_holds(in, (int)r0, (int)r1)) return FSR1_ERR_WINDOW;
+
+  EasuParams p;
+  p.in = view_of(in);
+  p.out = view_of(out);
+  p.c0x = as_float(con[0]); p.c0y = as_float(con[1]); p.c0z = as_float(con[2]); p.c0w = as_float(con[3]);
+  p.y0 = (int)y0; p.y1 = (int)y1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
+  cudaError_t e = cudaErrorNotSupported;
+  const char* name = "";
+  if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) e = launch_easu_h_tiled(p, s, &name);
+  if (e == cudaErrorNotSupported) e = launch_easu_direct(p, (int)in->format, exact, s, &name);
+  if (e != cudaSuccess) return cuda_fail(e);
+  t_last_kernel = name;
+  g_launches.fetch_add(1);
+  return FSR1_OK;
+}
+
+int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4], uint32_t y0, uint32_t y1,
+              uint32_t flags, void* stream) {
+  int rc;
+  if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
+  if (!con) return FSR1_ERR_INVALID_ARGUMENT;
+  if (in->format != out->format) return FSR1_ERR_UNSUPPORTED;
+  if (in->width != out->width || in->height != out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (y1 == 0) y1 = out->height;
+  if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!window_holds(out, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
+  const int need0 = y0 == 0 ? 0 : (int)y0 - 1, need1 = y1 >= out->height ? (int)out->height - 1 : (int)y1;
+  if (!window_holds(in, need0, need1)) return FSR1_ERR_WINDOW;
+
+  RcasParams p;
+  p.in = view_of(in);
+  p.out = view_of(out);
+  p.sharp = as_float(con[0]);
+  p.sharp_h2 = con[1];
+  p.y0 = (int)y0; p.y1 = (int)y1;
+  p.clamp = (flags & FSR1_FLAG_RCAS_CLAMP) ? 1 : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
+  cudaError_t e = cudaErrorNotSupported;
+  const char* name = "";
+  if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) e = launch_rcas_h_packed(p, s, &name);
+  if (e == cudaErrorNotSupported) e = launch_rcas_direct(p, (int)in->format, exact, s, &name);
+  if (e != cudaSuccess) return cuda_fail(e);
+  t_last_kernel = name;
+  g_launches.fetch_add(1);
+  return FSR1_OK;
+}
+
+int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* out, const uint32_t easu_con[16],
+                 const uint32_t rcas_con[4], uint32_t y0, uint32_t y1, uint32_t flags, void* stream) {
+  if (!out) return FSR1_ERR_INVALID_ARGUMENT;
+  if (y1 == 0) y1 = out->height;
+  if (flags & FSR1_FLAG_NO_RCAS) return fsr1_easu(in, out, easu_con, y0, y1, flags, stream);
+  if (!tmp) return FSR1_ERR_INVALID_ARGUMENT;
+  // EASU also produces the one-row apron RCAS reads, so a row slab needs no second exchange
+  const uint32_t e0 = y0 == 0 ? 0 : y0 - 1, e1 = y1 >= out->height ? out->height : y1 + 1;
+  int rc = fsr1_easu(in, tmp, easu_con, e0, e1, flags, stream);
+  if (rc != FSR1_OK) return rc;
+  return fsr1_rcas(tmp, out, rcas_con, y0, y1, flags, stream);
+}
+
+// ---- context --------------------------------------------------------------------------------------
+struct fsr1_context {
+  uint32_t in_w, in_h, out_w, out_h, format;
+  void* tmp;          // intermediate, out_w x out_h
+  uint64_t tmp_pitch;
+  void* dev_in;       // staging for the host-frame entry point (allocated on first use)
+  void* dev_out;
+  uint64_t in_pitch, out_pitch;
+};
+
+int fsr1_context_create(fsr1_context** ctx, uint32_t in_w, uint32_t in_h, uint32_t out_w, uint32_t out_h,
+                        uint32_t format) {
+  if (!ctx || !in_w || !in_h || !out_w || !out_h || !bytes_per_pixel(format)) return FSR1_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FSR1_ERR_NO_DEVICE;
+  fsr1_context* c = new (std::nothrow) fsr1_context();
+  if (!c) return FSR1_ERR_INVALID_ARGUMENT;
+  memset(c, 0, sizeof *c);
+  c->in_w = in_w; c->in_h = in_h; c->out_w = out_w; c->out_h = out_h; c->format = format;
+  const uint64_t bpp = (uint64_t)bytes_per_pixel(format);
+  c->tmp_pitch = ((uint64_t)out_w * bpp + 127) & ~(uint64_t)127;
+  cudaError_t e = cudaMalloc(&c->tmp, c->tmp_pitch * out_h);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e); }
+  *ctx = c;
+  return FSR1_OK;
+}
+
+void fsr1_context_destroy(fsr1_context* c) {
+  if (!c) return;
+  cudaFree(c->tmp);
+  cudaFree(c->dev_in);
+  cudaFree(c->dev_out);
+  delete c;
+}
+
+static int context_run(fsr1_context* c, void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
+                       float sharpness, uint32_t flags, void* stream) {
+  fsr1_image in = {in_dev, in_pitch, c->in_w, c->in_h, 0, c->in_h, c->format, 0};
+  fsr1_image tmp = {c->tmp, c->tmp_pitch, c->out_w, c->out_h, 0, c->out_h, c->format, 0};
+  fsr1_image out = {out_dev, out_pitch, c->out_w, c->out_h, 0, c->out_h, c->format, 0};
+  uint32_t econ[16], rcon[4];
+  // exactly what FSR_Filter::Upscale passes (sample/src/DX12/FSR_Filter.cpp:106,124)
+  fsr1_easu_con(econ, (float)c->in_w, (float)c->in_h, (float)c->in_w, (float)c->in_h, (float)c->out_w, (float)c->out_h);
+  fsr1_rcas_con(rcon, sharpness);
+  return fsr1_upscale(&in, &tmp, &out, econ, rcon, 0, c->out_h, flags, stream);
+}
+
+int fsr1_context_upscale(fsr1_context* c, const void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
+                         float sharpness, uint32_t flags, void* stream) {
+  if (!c || !in_dev || !out_dev) return FSR1_ERR_INVALID_ARGUMENT;
+  return context_run(c, const_cast<void*>(in_dev), in_pitch, out_dev, out_pitch, sharpness, flags, stream);
+}
+
+int fsr1_context_upscale_host(fsr1_context* c, const void* in_host, uint64_t in_pitch, void* out_host,
+                              uint64_t out_pitch, float sharpness, uint32_t flags, void* stream) {
+  if (!c || !in_host || !out_host) return FSR1_ERR_INVALID_ARGUMENT;
+  const uint64_t bpp = (uint64_t)bytes_per_pixel(c->format);
+  if (in_pitch < c->in_w * bpp || out_pitch < c->out_w * bpp) return FSR1_ERR_INVALID_ARGUMENT;
+  cudaError_t e;
+  if (!c->dev_in) {
+    c->in_pitch = ((uint64_t)c->in_w * bpp + 127) & ~(uint64_t)127;
+    c->out_pitch = ((uint64_t)c->out_w * bpp + 127) & ~(uint64_t)127;
+    if ((e = cudaMalloc(&c->dev_in, c->in_pitch * c->in_h)) != cudaSuccess) return cuda_fail(e);
+    if ((e = cudaMalloc(&c->dev_out, c->out_pitch * c->out_h)) != cudaSuccess) return cuda_fail(e);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  e = cudaMemcpy2DAsync(c->dev_in, c->in_pitch, in_host, in_pitch, c->in_w * bpp, c->in_h, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  int rc = context_run(c, c->dev_in, c->in_pitch, c->dev_out, c->out_pitch, sharpness, flags, stream);
+  if (rc != FSR1_OK) return rc;
+  e = cudaMemcpy2DAsync(out_host, out_pitch, c->dev_out, c->out_pitch, c->out_w * bpp, c->out_h, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return FSR1_OK;
+}
+
+}  // extern "C"

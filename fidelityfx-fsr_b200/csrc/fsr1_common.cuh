@@ -1,0 +1,105 @@
+// fsr1_common.cuh — shared device-side definitions of the B200 FSR1 kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fsr1 {
+
+// Device view of an fsr1_image (include/fsr1_b200.h): logical size w x h, storage holds rows
+// [row0, row0+rows).  `base` already points at logical row `row0`.
+struct ImgView {
+  unsigned char* base;
+  long long pitch;  // bytes
+  int w, h;         // logical size
+  int row0, rows;   // stored window
+};
+
+struct EasuParams {
+  ImgView in, out;
+  float c0x, c0y, c0z, c0w;  // con0 of FsrEasuCon: scale.xy, offset.zw
+  int y0, y1;                // output rows [y0,y1)
+};
+
+struct RcasParams {
+  ImgView in, out;
+  float sharp;      // con.x as float
+  uint32_t sharp_h2;  // con.y: half2(sharp,sharp)
+  int y0, y1;
+  int clamp;        // 0: out-of-image taps read 0 (D3D12 Load), 1: clamp
+};
+
+// ---- the reference's bit-trick approximations (ffx-fsr/ffx_a.h:1843-1845), bit-exact ------------
+__device__ __forceinline__ float prx_lo_rcp(float a) { return __uint_as_float(0x7ef07ebbu - __float_as_uint(a)); }
+__device__ __forceinline__ float prx_lo_rsq(float a) { return __uint_as_float(0x5f347d74u - (__float_as_uint(a) >> 1)); }
+
+// Arithmetic policy.  Exact: every product and sum rounds separately (no FMA contraction) and
+// reciprocals are IEEE, so the result is bit-identical to the reference source compiled with
+// -ffp-contract=off.  Fast: the compiler may contract a*b+c into FMA (what a shader compiler does).
+template <bool kExact> struct Ar;
+template <> struct Ar<true> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mad(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+  static __device__ __forceinline__ float rcp(float a) { return __fdiv_rn(1.0f, a); }
+};
+template <> struct Ar<false> {
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
+};
+
+__device__ __forceinline__ float sat(float x) { return __saturatef(x); }  // saturate(NaN) = 0
+
+// Output pixel -> (cell origin, fraction).  Always mul then add (two roundings): this is what the
+// oracle does, and the footprint computed on the host must agree with it for every pixel.
+__device__ __forceinline__ void easu_pos(int o, float scale, float offset, int& fp, float& pp) {
+  float p = __fadd_rn(__fmul_rn((float)o, scale), offset);
+  float f = floorf(p);
+  fp = (int)f;
+  pp = __fsub_rn(p, f);
+}
+
+// ---- storage access ------------------------------------------------------------------------------
+template <typename S> struct Px;
+template <> struct Px<float> {
+  static constexpr int kBytes = 16;
+  static __device__ __forceinline__ float3 load(const ImgView& im, int x, int y) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return make_float3(v.x, v.y, v.z);
+  }
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b) {
+    reinterpret_cast<float4*>(im.base + (long long)(y - im.row0) * im.pitch)[x] = make_float4(r, g, b, 1.0f);
+  }
+};
+template <> struct Px<__half> {
+  static constexpr int kBytes = 8;
+  static __device__ __forceinline__ float3 load(const ImgView& im, int x, int y) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float3(rg.x, rg.y, ba.x);
+  }
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b) {
+    __half2 rg = __floats2half2_rn(r, g), ba = __floats2half2_rn(b, 1.0f);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&rg);
+    v.y = *reinterpret_cast<uint32_t*>(&ba);
+    reinterpret_cast<uint2*>(im.base + (long long)(y - im.row0) * im.pitch)[x] = v;
+  }
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// launchers (defined in the .cu files, called from fsr1_capi.cu)
+cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name);
+cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cudaStream_t s, const char** name);
+// Packed-half production kernels.  Return cudaErrorNotSupported when the image layout does not
+// meet their alignment needs (the caller then falls back to the direct kernels).
+cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name);
+cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name);
+
+}  // namespace fsr1

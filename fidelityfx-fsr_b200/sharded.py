@@ -1,0 +1,133 @@
+"""Row-slab sharding of the EASU+RCAS path across the GPUs of one box.
+
+The reference has no multi-GPU path; this is new.  Every output pixel depends on a bounded input
+neighbourhood, so the OUTPUT is cut into G contiguous row slabs, rank k owns input rows
+[k*inH/G, (k+1)*inH/G) and needs a few more rows above/below (the EASU footprint of its output slab
+extended by one output row each side, so that RCAS's +-1-row taps need no second exchange).
+The only communication is that halo: point-to-point rows between neighbouring ranks
+(torch.distributed batch_isend_irecv -> ncclSend/ncclRecv over NVLink); there is no collective and a
+1-GPU run issues no communication at all.
+
+SlabPlan is pure integer geometry (unit-tested on CPU); ShardedUpscaler moves the rows and launches
+the kernels through the C ABI with image *windows* (row0/rows), so clamping at the true image
+border and reading halo rows at slab borders are both handled by the same kernels.
+"""
+import math
+
+import numpy as np
+
+from . import api
+
+
+def _cell(o, scale, offset):
+    """floor(o*scale+offset) in the kernels' float arithmetic (mul and add rounded separately)."""
+    return int(math.floor(np.float32(np.float32(np.float32(o) * np.float32(scale)) + np.float32(offset))))
+
+
+class SlabPlan:
+    def __init__(self, in_h, out_h, world, easu_con):
+        self.in_h, self.out_h, self.world = int(in_h), int(out_h), int(world)
+        self.scale = np.array([easu_con[1]], dtype=np.uint32).view(np.float32)[0]
+        self.offset = np.array([easu_con[3]], dtype=np.uint32).view(np.float32)[0]
+
+    def out_rows(self, rank):
+        """Output rows [y0,y1) of this rank's slab."""
+        return rank * self.out_h // self.world, (rank + 1) * self.out_h // self.world
+
+    def easu_rows(self, rank):
+        """EASU is run for the slab plus a one-row apron (what RCAS reads)."""
+        y0, y1 = self.out_rows(rank)
+        return max(y0 - 1, 0), min(y1 + 1, self.out_h)
+
+    def owned_in_rows(self, rank):
+        return rank * self.in_h // self.world, (rank + 1) * self.in_h // self.world
+
+    def needed_in_rows(self, rank):
+        """Input rows [r0,r1) the rank's EASU pass reads (clamped to the image)."""
+        e0, e1 = self.easu_rows(rank)
+        if e1 <= e0:
+            return 0, 0
+        lo = _cell(e0, self.scale, self.offset) - 1
+        hi = _cell(e1 - 1, self.scale, self.offset) + 2
+        lo = min(max(lo, 0), self.in_h - 1)
+        hi = min(max(hi, 0), self.in_h - 1)
+        return lo, hi + 1
+
+    def transfers(self, rank):
+        """(sends, recvs): lists of (peer, first_row, end_row) in logical input rows."""
+        sends, recvs = [], []
+        own0, own1 = self.owned_in_rows(rank)
+        need0, need1 = self.needed_in_rows(rank)
+        for peer in range(self.world):
+            if peer == rank:
+                continue
+            p_own0, p_own1 = self.owned_in_rows(peer)
+            p_need0, p_need1 = self.needed_in_rows(peer)
+            a, b = max(own0, p_need0), min(own1, p_need1)      # my rows the peer needs
+            if b > a:
+                sends.append((peer, a, b))
+            a, b = max(p_own0, need0), min(p_own1, need1)      # the peer's rows I need
+            if b > a:
+                recvs.append((peer, a, b))
+        return sends, recvs
+
+    def halo_bytes(self, rank, width, bytes_per_pixel):
+        return sum((b - a) * width * bytes_per_pixel for _, a, b in self.transfers(rank)[1])
+
+
+def exchange_halo(plan, rank, owned, window, dist=None):
+    """Fill `window` (rows needed_in_rows(rank)) from `owned` (rows owned_in_rows(rank)) and the peers.
+
+    Works on any backend: gloo with CPU tensors (tests) or nccl with CUDA tensors (production).
+    """
+    own0, own1 = plan.owned_in_rows(rank)
+    need0, need1 = plan.needed_in_rows(rank)
+    a, b = max(own0, need0), min(own1, need1)
+    if b > a:
+        window[a - need0:b - need0].copy_(owned[a - own0:b - own0])
+    sends, recvs = plan.transfers(rank)
+    if not sends and not recvs:
+        return 0
+    if dist is None:
+        import torch.distributed as dist
+    ops = []
+    for peer, r0, r1 in sends:
+        ops.append(dist.P2POp(dist.isend, owned[r0 - own0:r1 - own0], peer))
+    for peer, r0, r1 in recvs:
+        ops.append(dist.P2POp(dist.irecv, window[r0 - need0:r1 - need0], peer))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return len(ops)
+
+
+class ShardedUpscaler:
+    """One instance per rank (one process per GPU)."""
+
+    def __init__(self, in_w, in_h, out_w, out_h, world, rank, sharpness=0.25, dtype=None, device=None, flags=0):
+        import torch
+        self.rank, self.world = rank, world
+        self.in_w, self.in_h, self.out_w, self.out_h = in_w, in_h, out_w, out_h
+        self.econ = api.easu_con(in_w, in_h, in_w, in_h, out_w, out_h)
+        self.rcon = api.rcas_con(sharpness)
+        self.plan = SlabPlan(in_h, out_h, world, self.econ)
+        self.flags = flags
+        dtype = dtype or torch.float16
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        n0, n1 = self.plan.needed_in_rows(rank)
+        e0, e1 = self.plan.easu_rows(rank)
+        y0, y1 = self.plan.out_rows(rank)
+        self.window = torch.empty((n1 - n0, in_w, 4), dtype=dtype, device=device)
+        self.tmp = torch.empty((e1 - e0, out_w, 4), dtype=dtype, device=device)
+        self.out = torch.empty((y1 - y0, out_w, 4), dtype=dtype, device=device)
+
+    def upscale(self, owned_rows, stream=None):
+        """owned_rows: this rank's input slab [owned_in_rows) on the GPU.  Returns the output slab."""
+        plan, rank = self.plan, self.rank
+        exchange_halo(plan, rank, owned_rows, self.window)
+        n0, _ = plan.needed_in_rows(rank)
+        e0, _ = plan.easu_rows(rank)
+        y0, y1 = plan.out_rows(rank)
+        api.upscale(api.image(self.window, height=self.in_h, row0=n0), api.image(self.tmp, height=self.out_h, row0=e0),
+                    api.image(self.out, height=self.out_h, row0=y0), self.econ, self.rcon, y0=y0, y1=y1,
+                    flags=self.flags, stream=stream)
+        return self.out

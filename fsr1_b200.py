@@ -1,0 +1,12 @@
+"""Import alias: `import fsr1_b200` loads the package directory `fidelityfx-fsr_b200/` (whose name, with a
+hyphen, cannot be written in an import statement)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fidelityfx-fsr_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

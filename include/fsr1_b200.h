@@ -1,0 +1,130 @@
+/* fsr1_b200.h — C ABI of the B200-native FSR 1.0 hot path (EASU upsample + RCAS sharpen).
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types appear in any signature (a stream is
+ * passed as void* = cudaStream_t, NULL = the legacy default stream).  This is what a binding in
+ * the reference's host code (or any FFI: ctypes, cgo, JNI ...) attaches to; see INTEGRATION.md.
+ *
+ * What each entry point replaces in the reference (GPUOpen-Effects/FidelityFX-FSR):
+ *   fsr1_easu      the EASU dispatch: shader FsrEasuF/FsrEasuH (ffx-fsr/ffx_fsr1.h:315-437, 505-593)
+ *                  entered from mainCS/CurrFilter (sample/src/DX12/FSR_Pass.hlsl:68-118), recorded by
+ *                  FSR_Filter::Upscale -> m_easu.Draw (sample/src/DX12/FSR_Filter.cpp:121,135)
+ *   fsr1_rcas      the RCAS dispatch: FsrRcasF/FsrRcasH (ffx-fsr/ffx_fsr1.h:684-769, 782-866),
+ *                  m_rcas.Draw (sample/src/DX12/FSR_Filter.cpp:131)
+ *   fsr1_upscale   the whole of FSR_Filter::Upscale (sample/src/DX12/FSR_Filter.cpp:101-141):
+ *                  EASU -> (barrier) -> RCAS through a display-sized intermediate
+ *   fsr1_context_* FSR_Filter::OnCreateWindowSizeDependentResources / OnDestroy... (FSR_Filter.cpp:70-99):
+ *                  owns the intermediate image (and, for the *_host call, device staging buffers)
+ *   fsr1_upscale_host  same as fsr1_upscale for callers whose frames live in HOST memory: copies the
+ *                  input up, runs both passes, copies the result back, all on one stream
+ * The constant blocks (con0..con3, rcas con) are EXACTLY the uint32[4] words FsrEasuCon /
+ * FsrEasuConOffset / FsrRcasCon produce (include/fsr1_host.h, or the reference's own header).
+ *
+ * Semantics fixed by the reference and reproduced here:
+ *   - images are row-major RGBA, 4 x fp16 (FSR1_FORMAT_RGBA16F, the reference's rgba16f path) or
+ *     4 x fp32 (FSR1_FORMAT_RGBA32F, the SAMPLE_SLOW_FALLBACK path); EASU/RCAS read RGB, ignore A,
+ *     and store A = 1 (FSR_Pass.hlsl:80,95)
+ *   - EASU taps are clamped to the edge of the input RESOURCE (linear/clamp sampler, FSR_Filter.cpp:48-53)
+ *   - RCAS taps outside the image read 0 (D3D12 Load); FSR1_FLAG_RCAS_CLAMP selects clamp instead
+ *   - fp32 images run the F algorithm in fp32; fp16 images run a packed-half implementation whose
+ *     results stay within 1e-2 of the fp32 algorithm on the same (quantised) input
+ * All launch calls are asynchronous with respect to the host and allocate nothing
+ * (fsr1_context_create and fsr1_upscale_host's first use are the only allocating calls).
+ * Thread-safe for distinct contexts/streams.  Every function returns FSR1_OK or a negative fsr1 error;
+ * CUDA failures are reported as FSR1_ERR_CUDA and the CUDA error is kept for fsr1_last_cuda_error().
+ */
+#ifndef FSR1_B200_H
+#define FSR1_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSR1_ABI_VERSION 1
+
+enum {
+  FSR1_OK = 0,
+  FSR1_ERR_INVALID_ARGUMENT = -1, /* null pointer, zero size, bad row range, unknown format/flag   */
+  FSR1_ERR_UNSUPPORTED = -2,      /* format combination the kernels do not implement              */
+  FSR1_ERR_WINDOW = -3,           /* an image window (row0/rows) does not hold the rows the pass reads/writes */
+  FSR1_ERR_CUDA = -4,             /* a CUDA call failed; see fsr1_last_cuda_error()                */
+  FSR1_ERR_NO_DEVICE = -5         /* no usable sm_100 device / driver                              */
+};
+
+enum { FSR1_FORMAT_RGBA16F = 1, FSR1_FORMAT_RGBA32F = 2 };
+
+enum {
+  FSR1_FLAG_RCAS_CLAMP = 1u << 0,   /* RCAS out-of-image taps clamp instead of reading 0               */
+  FSR1_FLAG_EXACT = 1u << 1,        /* fp32 images only: no FMA contraction, IEEE division — bit-identical
+                                       to the reference source compiled with -ffp-contract=off          */
+  FSR1_FLAG_FORCE_DIRECT = 1u << 2, /* skip the TMA/shared-memory kernels, use the direct-load kernels   */
+  FSR1_FLAG_NO_RCAS = 1u << 3       /* fsr1_upscale*: EASU straight to the output (bUseRcas == false)   */
+};
+
+/* A (window of a) device image.  `width`/`height` are the logical size of the whole image; `data`
+ * points at logical row `row0` and holds `rows` rows (row0 = 0, rows = height for a whole image).
+ * Windows exist for row-slab sharding: a GPU holds only the rows it needs (plus halo) but clamping and
+ * out-of-image rules still refer to the whole image.  pitch_bytes >= width * bytes-per-pixel. */
+typedef struct fsr1_image {
+  void* data;
+  uint64_t pitch_bytes;
+  uint32_t width, height;
+  uint32_t row0, rows;
+  uint32_t format;
+  uint32_t reserved;
+} fsr1_image;
+
+/* EASU over output rows [y0, y1) (y1 == 0 means "to the last row").  con = con0..con3, 16 words. */
+int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16], uint32_t y0, uint32_t y1,
+              uint32_t flags, void* stream);
+
+/* RCAS over rows [y0, y1); in and out have the same logical size and format.  con = 4 words. */
+int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4], uint32_t y0, uint32_t y1,
+              uint32_t flags, void* stream);
+
+/* First and last input row EASU reads to produce output rows [y0,y1) (clamped to the image): what a
+ * slab must hold, and what must be exchanged as halo when the output is sharded by rows. */
+int fsr1_easu_input_rows(const uint32_t con[16], uint32_t in_height, uint32_t y0, uint32_t y1,
+                         uint32_t* first_row, uint32_t* last_row);
+
+/* EASU -> RCAS for output rows [y0,y1).  `tmp` is the display-sized intermediate (same format as out);
+ * it must hold rows [y0-1, y1+1) clipped to the image.  easu_con 16 words, rcas_con 4 words. */
+int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* out, const uint32_t easu_con[16],
+                 const uint32_t rcas_con[4], uint32_t y0, uint32_t y1, uint32_t flags, void* stream);
+
+/* ---- resource-owning context (the FSR_Filter object of the sample) ---------------------------- */
+typedef struct fsr1_context fsr1_context;
+
+/* Allocates the intermediate image for (out_width x out_height, format) on the current device. */
+int fsr1_context_create(fsr1_context** ctx, uint32_t in_width, uint32_t in_height, uint32_t out_width,
+                        uint32_t out_height, uint32_t format);
+void fsr1_context_destroy(fsr1_context* ctx);
+
+/* Device-resident frames: constants are derived inside exactly as FSR_Filter::Upscale does
+ * (FsrEasuCon(renderW,renderH,renderW,renderH,displayW,displayH); FsrRcasCon(sharpness_stops)). */
+int fsr1_context_upscale(fsr1_context* ctx, const void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
+                         float sharpness_stops, uint32_t flags, void* stream);
+
+/* Host-resident frames (pinned memory recommended): H2D copy, EASU, RCAS, D2H copy on `stream`. */
+int fsr1_context_upscale_host(fsr1_context* ctx, const void* in_host, uint64_t in_pitch, void* out_host,
+                              uint64_t out_pitch, float sharpness_stops, uint32_t flags, void* stream);
+
+/* ---- constants through the ABI (for FFIs that cannot include fsr1_host.h) ---------------------- */
+void fsr1_easu_con(uint32_t con[16], float in_viewport_w, float in_viewport_h, float in_size_w, float in_size_h,
+                   float out_w, float out_h);
+void fsr1_easu_con_offset(uint32_t con[16], float in_viewport_w, float in_viewport_h, float in_size_w,
+                          float in_size_h, float out_w, float out_h, float in_off_x, float in_off_y);
+void fsr1_rcas_con(uint32_t con[4], float sharpness_stops);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+int fsr1_abi_version(void);
+const char* fsr1_error_string(int err);
+int fsr1_last_cuda_error(void);          /* cudaError_t of the last failed CUDA call on this thread   */
+uint64_t fsr1_launch_count(void);        /* kernels launched by this library since load (all threads) */
+const char* fsr1_last_kernel_name(void); /* which kernel variant the last launch on this thread used  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSR1_B200_H */

@@ -1,0 +1,168 @@
+// TEST INFRASTRUCTURE — not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load the library built from this file.
+//
+// Host driver around the reference's OWN per-pixel source.  build_ref.sh produces, in a temp
+// directory, a mechanically rewritten copy of /root/reference/ffx-fsr/{ffx_a.h,ffx_fsr1.h}
+// (parameter qualifiers `in/out/inout` -> C++ value/reference; nothing else) and compiles this
+// file against it with oracle/shim/hlsl_on_cpp.h standing in for the HLSL vector language.
+// The statements executed per pixel are therefore the reference's own, in their own order:
+//   FsrEasuF  ffx-fsr/ffx_fsr1.h:315-437     FsrRcasF  ffx-fsr/ffx_fsr1.h:684-769
+//   FsrEasuH  ffx-fsr/ffx_fsr1.h:505-593     FsrRcasH  ffx-fsr/ffx_fsr1.h:782-866
+// The callbacks below mirror the sample's shader wrapper:
+//   gather4 + linear/clamp sampler   sample/src/DX12/FSR_Pass.hlsl:39-41,55-57, FSR_Filter.cpp:48-53
+//   integer Load (OOB -> 0 in D3D12) sample/src/DX12/FSR_Pass.hlsl:45-46,61-62
+//   store float4(c,1)                sample/src/DX12/FSR_Pass.hlsl:80,86,95,101
+#include "hlsl_on_cpp.h"
+
+#define A_GPU 1
+#define A_HLSL 1
+#ifdef FSR1_REF_HALF
+#define A_HALF 1
+#endif
+#include "ffx_a.h"  // rewritten copy, found through -I<tmpdir>
+
+struct ImgF { const float* p; int w, h; size_t pitch; };        // RGBA32F, pitch in floats
+struct ImgH { const uint16_t* p; int w, h; size_t pitch; };     // RGBA16F, pitch in halves
+static thread_local ImgF g_f;
+static thread_local int g_rcas_clamp;
+#ifdef FSR1_REF_HALF
+static thread_local ImgH g_h;
+#endif
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// gather4 of channel c at normalised p: (x,y,z,w) = texels (i,j+1),(i+1,j+1),(i+1,j),(i,j)
+static inline AF4 gatherF(AF2 p, int c) {
+  int i = (int)floorf(p.x * (float)g_f.w - 0.5f), j = (int)floorf(p.y * (float)g_f.h - 0.5f);
+  int x0 = clampi(i, 0, g_f.w - 1), x1 = clampi(i + 1, 0, g_f.w - 1);
+  int y0 = clampi(j, 0, g_f.h - 1), y1 = clampi(j + 1, 0, g_f.h - 1);
+  const float* b = g_f.p;
+  return AF4(b[y1 * g_f.pitch + x0 * 4 + c], b[y1 * g_f.pitch + x1 * 4 + c],
+             b[y0 * g_f.pitch + x1 * 4 + c], b[y0 * g_f.pitch + x0 * 4 + c]);
+}
+#define FSR_EASU_F 1
+AF4 FsrEasuRF(AF2 p) { return gatherF(p, 0); }
+AF4 FsrEasuGF(AF2 p) { return gatherF(p, 1); }
+AF4 FsrEasuBF(AF2 p) { return gatherF(p, 2); }
+#define FSR_RCAS_F 1
+AF4 FsrRcasLoadF(ASU2 p) {
+  int x = p.x, y = p.y;
+  if (g_rcas_clamp) { x = clampi(x, 0, g_f.w - 1); y = clampi(y, 0, g_f.h - 1); }
+  else if (x < 0 || y < 0 || x >= g_f.w || y >= g_f.h) return AF4(0.0f, 0.0f, 0.0f, 0.0f);
+  const float* t = g_f.p + y * g_f.pitch + x * 4;
+  return AF4(t[0], t[1], t[2], t[3]);
+}
+void FsrRcasInputF(AF1& r, AF1& g, AF1& b) {}
+
+#ifdef FSR1_REF_HALF
+static inline _Float16 h_from_bits(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return h; }
+static inline uint16_t h_to_bits(_Float16 h) { uint16_t b; memcpy(&b, &h, 2); return b; }
+static inline AH4 gatherH(AF2 p, int c) {
+  int i = (int)floorf(p.x * (float)g_h.w - 0.5f), j = (int)floorf(p.y * (float)g_h.h - 0.5f);
+  int x0 = clampi(i, 0, g_h.w - 1), x1 = clampi(i + 1, 0, g_h.w - 1);
+  int y0 = clampi(j, 0, g_h.h - 1), y1 = clampi(j + 1, 0, g_h.h - 1);
+  const uint16_t* b = g_h.p;
+  return AH4(h_from_bits(b[y1 * g_h.pitch + x0 * 4 + c]), h_from_bits(b[y1 * g_h.pitch + x1 * 4 + c]),
+             h_from_bits(b[y0 * g_h.pitch + x1 * 4 + c]), h_from_bits(b[y0 * g_h.pitch + x0 * 4 + c]));
+}
+#define FSR_EASU_H 1
+AH4 FsrEasuRH(AF2 p) { return gatherH(p, 0); }
+AH4 FsrEasuGH(AF2 p) { return gatherH(p, 1); }
+AH4 FsrEasuBH(AF2 p) { return gatherH(p, 2); }
+#define FSR_RCAS_H 1
+AH4 FsrRcasLoadH(ASW2 p) {
+  int x = p.x, y = p.y;
+  if (g_rcas_clamp) { x = clampi(x, 0, g_h.w - 1); y = clampi(y, 0, g_h.h - 1); }
+  else if (x < 0 || y < 0 || x >= g_h.w || y >= g_h.h) return AH4(0.0f, 0.0f, 0.0f, 0.0f);
+  const uint16_t* t = g_h.p + y * g_h.pitch + x * 4;
+  return AH4(h_from_bits(t[0]), h_from_bits(t[1]), h_from_bits(t[2]), h_from_bits(t[3]));
+}
+void FsrRcasInputH(AH1& r, AH1& g, AH1& b) {}
+#endif
+
+#include "ffx_fsr1.h"  // rewritten copy
+
+extern "C" {
+
+// Constants as the reference computes them in its A_GPU build (FsrRcasCon's packed half uses
+// round-to-nearest f32tof16 here; the A_CPU build truncates — see ref_cpu.c for that one).
+void fsr1ref_gpu_easu_con(uint32_t* con /*16*/, float inVpW, float inVpH, float inW, float inH, float outW, float outH) {
+  AU4 c0, c1, c2, c3;
+  FsrEasuCon(c0, c1, c2, c3, inVpW, inVpH, inW, inH, outW, outH);
+  for (int i = 0; i < 4; i++) { con[i] = c0[i]; con[4 + i] = c1[i]; con[8 + i] = c2[i]; con[12 + i] = c3[i]; }
+}
+void fsr1ref_gpu_rcas_con(uint32_t* con /*4*/, float sharpness) {
+  AU4 c; FsrRcasCon(c, sharpness);
+  for (int i = 0; i < 4; i++) con[i] = c[i];
+}
+
+// EASU fp32 over output rows [y0,y1).  Images are RGBA32F, pitches in floats.
+void fsr1ref_easu_f(const float* in, int inW, int inH, size_t inPitch, float* out, int outW, int outH,
+                    size_t outPitch, const uint32_t* con, int y0, int y1) {
+  AU4 c0(con[0], con[1], con[2], con[3]), c1(con[4], con[5], con[6], con[7]);
+  AU4 c2(con[8], con[9], con[10], con[11]), c3(con[12], con[13], con[14], con[15]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = y0; y < y1; y++) {
+    g_f = ImgF{in, inW, inH, inPitch};
+    for (int x = 0; x < outW; x++) {
+      AF3 pix;
+      FsrEasuF(pix, AU2((uint)x, (uint)y), c0, c1, c2, c3);
+      float* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      o[0] = pix.r; o[1] = pix.g; o[2] = pix.b; o[3] = 1.0f;
+    }
+  }
+}
+
+// RCAS fp32 over rows [y0,y1); oob_clamp=0 -> D3D12 Load semantics (OOB reads 0), 1 -> clamp.
+void fsr1ref_rcas_f(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
+                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+  AU4 c(con[0], con[1], con[2], con[3]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = y0; y < y1; y++) {
+    g_f = ImgF{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
+    for (int x = 0; x < W; x++) {
+      AF1 r, g, b;
+      FsrRcasF(r, g, b, AU2((uint)x, (uint)y), c);
+      float* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      o[0] = r; o[1] = g; o[2] = b; o[3] = 1.0f;
+    }
+  }
+}
+
+#ifdef FSR1_REF_HALF
+// The packed-half variants: images are RGBA16F (raw half bits), pitches in halves.
+void fsr1ref_easu_h(const uint16_t* in, int inW, int inH, size_t inPitch, uint16_t* out, int outW, int outH,
+                    size_t outPitch, const uint32_t* con, int y0, int y1) {
+  AU4 c0(con[0], con[1], con[2], con[3]), c1(con[4], con[5], con[6], con[7]);
+  AU4 c2(con[8], con[9], con[10], con[11]), c3(con[12], con[13], con[14], con[15]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = y0; y < y1; y++) {
+    g_h = ImgH{in, inW, inH, inPitch};
+    for (int x = 0; x < outW; x++) {
+      AH3 pix;
+      FsrEasuH(pix, AU2((uint)x, (uint)y), c0, c1, c2, c3);
+      uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      o[0] = h_to_bits(pix.r); o[1] = h_to_bits(pix.g); o[2] = h_to_bits(pix.b); o[3] = 0x3c00;
+    }
+  }
+}
+void fsr1ref_rcas_h(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+  AU4 c(con[0], con[1], con[2], con[3]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = y0; y < y1; y++) {
+    g_h = ImgH{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
+    for (int x = 0; x < W; x++) {
+      AH1 r, g, b;
+      FsrRcasH(r, g, b, AU2((uint)x, (uint)y), c);
+      uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      o[0] = h_to_bits(r); o[1] = h_to_bits(g); o[2] = h_to_bits(b); o[3] = 0x3c00;
+    }
+  }
+}
+int fsr1ref_has_half(void) { return 1; }
+#else
+int fsr1ref_has_half(void) { return 0; }
+#endif
+
+}  // extern "C"

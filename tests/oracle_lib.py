@@ -1,0 +1,115 @@
+"""ctypes access to the CPU oracle (oracle/libfsr1_oracle.so) and, when it was built, to the reference's
+own source compiled for the host (oracle/_ref/libfsr1_ref.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libfsr1_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfsr1_ref.so")
+P, F, Z, U = ctypes.c_void_p, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint32
+
+
+def build():
+    src = os.path.join(ROOT, "oracle", "fsr1_oracle.c")
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libfsr1_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    if not os.path.exists(REF_SO) and os.path.exists("/root/reference/ffx-fsr/ffx_fsr1.h"):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")], stdout=subprocess.DEVNULL)
+
+
+_o = _r = None
+
+
+def oracle():
+    global _o
+    if _o is None:
+        build()
+        _o = ctypes.CDLL(ORACLE_SO)
+        _o.fsr1o_f32_to_f16_trunc.restype = ctypes.c_uint32
+        _o.fsr1o_f32_to_f16_trunc.argtypes = [F]
+    return _o
+
+
+def ref():
+    """The reference-source build, or None where it is not available."""
+    global _r
+    if _r is None:
+        build()
+        if not os.path.exists(REF_SO):
+            return None
+        _r = ctypes.CDLL(REF_SO)
+        _r.fsr1ref_cpu_f32_to_f16.restype = ctypes.c_uint32
+        _r.fsr1ref_cpu_f32_to_f16.argtypes = [F]
+    return _r
+
+
+def _con(n):
+    return (ctypes.c_uint32 * n)()
+
+
+def easu_con(iw, ih, ow, oh, vw=None, vh=None, lib=None, off=None):
+    c = _con(16)
+    vw, vh = (iw if vw is None else vw), (ih if vh is None else vh)
+    if lib is None or lib is oracle():
+        if off is None:
+            oracle().fsr1o_easu_con(c, F(vw), F(vh), F(iw), F(ih), F(ow), F(oh))
+        else:
+            oracle().fsr1o_easu_con_offset(c, F(vw), F(vh), F(iw), F(ih), F(ow), F(oh), F(off[0]), F(off[1]))
+    else:
+        if off is None:
+            lib.fsr1ref_cpu_easu_con(c, F(vw), F(vh), F(iw), F(ih), F(ow), F(oh))
+        else:
+            lib.fsr1ref_cpu_easu_con_offset(c, F(vw), F(vh), F(iw), F(ih), F(ow), F(oh), F(off[0]), F(off[1]))
+    return list(c)
+
+
+def rcas_con(sharp, lib=None):
+    c = _con(4)
+    if lib is None or lib is oracle():
+        oracle().fsr1o_rcas_con(c, F(sharp))
+    else:
+        lib.fsr1ref_cpu_rcas_con(c, F(sharp))
+    return list(c)
+
+
+def _arr(con):
+    return (ctypes.c_uint32 * len(con))(*con)
+
+
+def _pitch(a):
+    assert a.strides[2] == a.itemsize and a.strides[1] == 4 * a.itemsize
+    return a.strides[0] // a.itemsize
+
+
+def easu(img, ow, oh, con=None, y0=0, y1=None, lib=None):
+    """EASU of a [H,W,4] float32 (F path) or uint16/float16 (H-path model) image on the CPU."""
+    lib = lib or oracle()
+    ih, iw = img.shape[:2]
+    con = con or easu_con(iw, ih, ow, oh)
+    y1 = oh if y1 is None else y1
+    half = img.dtype != np.float32
+    src = img.view(np.uint16) if half else img
+    out = np.zeros((oh, ow, 4), np.uint16 if half else np.float32)
+    name = {(False, True): "fsr1o_easu_f32", (True, True): "fsr1o_easu_h16", (False, False): "fsr1ref_easu_f",
+            (True, False): "fsr1ref_easu_h"}[(half, lib is oracle())]
+    getattr(lib, name)(P(src.ctypes.data), iw, ih, Z(_pitch(src)), P(out.ctypes.data), ow, oh, Z(_pitch(out)), _arr(con),
+                       y0, y1)
+    return out.view(np.float16) if half else out
+
+
+def rcas(img, con, clamp=False, y0=0, y1=None, lib=None):
+    lib = lib or oracle()
+    h, w = img.shape[:2]
+    y1 = h if y1 is None else y1
+    half = img.dtype != np.float32
+    src = img.view(np.uint16) if half else img
+    out = np.zeros((h, w, 4), np.uint16 if half else np.float32)
+    name = {(False, True): "fsr1o_rcas_f32", (True, True): "fsr1o_rcas_h16", (False, False): "fsr1ref_rcas_f",
+            (True, False): "fsr1ref_rcas_h"}[(half, lib is oracle())]
+    getattr(lib, name)(P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con),
+                       1 if clamp else 0, y0, y1)
+    return out.view(np.float16) if half else out

@@ -1,0 +1,56 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/fsr1_b200.h declares; argument
+validation is exercised through paths that return before any CUDA call."""
+import ctypes
+import os
+import re
+
+import fsr1_b200 as F
+from fsr1_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fsr1_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsr1_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(L, n), "missing export: " + n
+    assert sorted(_lib.SYMBOLS) == names
+    assert L.fsr1_abi_version() == 1
+
+
+def test_error_strings_and_validation_without_gpu():
+    L = _lib.lib()
+    assert L.fsr1_error_string(0) == b"ok"
+    assert b"invalid" in L.fsr1_error_string(-1)
+    img = _lib.Image(0, 0, 0, 0, 0, 0, 1, 0)  # null data
+    con = (ctypes.c_uint32 * 16)()
+    assert L.fsr1_easu(ctypes.byref(img), ctypes.byref(img), con, 0, 0, 0, None) == -1
+    assert L.fsr1_rcas(ctypes.byref(img), ctypes.byref(img), con, 0, 0, 0, None) == -1
+    assert L.fsr1_upscale(None, None, None, con, con, 0, 0, 0, None) == -1
+    buf = (ctypes.c_uint8 * 4096)()
+    addr = ctypes.addressof(buf)
+    addr += (-addr) % 16
+    ok_in = _lib.Image(addr, 64, 8, 4, 0, 4, 1, 0)
+    bad_fmt = _lib.Image(addr, 64, 8, 4, 0, 4, 9, 0)
+    assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(bad_fmt), con, 0, 0, 0, None) == -1
+    f32_out = _lib.Image(addr, 256, 16, 8, 0, 8, 2, 0)
+    assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(f32_out), con, 0, 0, 0, None) == -2  # mixed formats
+    small_pitch = _lib.Image(addr, 32, 8, 4, 0, 4, 1, 0)
+    assert L.fsr1_easu(ctypes.byref(small_pitch), ctypes.byref(ok_in), con, 0, 0, 0, None) == -1
+    # window that does not hold the rows EASU would read -> FSR1_ERR_WINDOW, before any launch
+    econ = (ctypes.c_uint32 * 16)(*F.api.easu_con(8, 64, 8, 64, 16, 128))
+    win_in = _lib.Image(addr, 64, 8, 64, 10, 4, 1, 0)
+    out = _lib.Image(addr, 128, 16, 128, 0, 128, 1, 0)
+    assert L.fsr1_easu(ctypes.byref(win_in), ctypes.byref(out), econ, 0, 0, 0, None) == -3
+    a, b = ctypes.c_uint32(), ctypes.c_uint32()
+    assert L.fsr1_easu_input_rows(econ, 64, 20, 40, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (8, 21)  # rows floor((20+.5)/2-.5)-1 .. floor((39+.5)/2-.5)+2
+    assert L.fsr1_launch_count() == 0

@@ -1,0 +1,247 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8(d)):
+  fp32 images, FSR1_FLAG_EXACT : bit-exact to the oracle (reference source built with -ffp-contract=off)
+  fp32 images, default          : max-abs <= 1e-5
+  fp16 images                   : max-abs <= 1e-2 against the fp32 oracle reading the SAME half-quantised input
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fsr1_b200 as F
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+api = F.api
+TOL32, TOL16 = 1e-5, 1e-2
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fsr1_golden.npz"))
+GSIZES = {"x2.0": (64, 36), "x1.5": (48, 27), "x1.3": (41, 23), "x1.0": (32, 18), "x2.0x1.5": (64, 27)}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_easu(src, ow, oh, flags=0, con=None, y0=0, y1=0):
+    ih, iw = src.shape[:2]
+    con = con or api.easu_con(iw, ih, iw, ih, ow, oh)
+    out = torch.zeros((oh, ow, 4), dtype=torch.float16 if src.dtype == np.float16 else torch.float32, device="cuda")
+    api.easu(dev(src), out, con, y0=y0, y1=y1, flags=flags)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def gpu_rcas(src, sharp, flags=0, y0=0, y1=0):
+    out = torch.zeros(src.shape, dtype=torch.float16 if src.dtype == np.float16 else torch.float32, device="cuda")
+    api.rcas(dev(src), out, api.rcas_con(sharp), y0=y0, y1=y1, flags=flags)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+SHAPES = [(96, 54, 192, 108), (96, 54, 144, 81), (96, 54, 125, 70), (33, 17, 57, 31), (7, 5, 14, 10), (64, 64, 64, 64),
+          (3, 3, 9, 9), (1, 1, 4, 4), (50, 20, 65, 26), (130, 70, 259, 141), (200, 40, 401, 79)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_fp32_exact_is_bit_identical(shape, gen):
+    iw, ih, ow, oh = shape
+    src = getattr(F, gen)(iw, ih, 31)
+    want = ol.easu(src, ow, oh)
+    got = gpu_easu(src, ow, oh, api.FLAG_EXACT)
+    assert api.last_kernel().startswith("easu_direct<f32,exact")
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    for clamp in (0, api.FLAG_RCAS_CLAMP):
+        for sharp in (0.0, 0.25, 1.0):
+            r = gpu_rcas(want, sharp, api.FLAG_EXACT | clamp)
+            assert np.array_equal(r.view(np.uint32), ol.rcas(want, ol.rcas_con(sharp), bool(clamp)).view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_fp32_default_within_1e5(shape, gen):
+    iw, ih, ow, oh = shape
+    src = getattr(F, gen)(iw, ih, 32)
+    want = ol.easu(src, ow, oh)
+    got = gpu_easu(src, ow, oh)
+    assert np.abs(got - want).max() <= TOL32
+    r = gpu_rcas(want, 0.25)
+    assert np.abs(r - ol.rcas(want, ol.rcas_con(0.25))).max() <= TOL32
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_fp16_kernels_within_1e2_of_fp32_oracle(shape, gen):
+    iw, ih, ow, oh = shape
+    src = F.to_half(getattr(F, gen)(iw, ih, 33))
+    want = ol.easu(src.astype(np.float32), ow, oh)       # fp32 algorithm on the quantised input
+    got = gpu_easu(src, ow, oh)
+    assert api.last_kernel().startswith("easu_h_tiled"), api.last_kernel()
+    assert got.dtype == np.float16 and np.all(got[..., 3] == 1.0)
+    assert np.abs(got.astype(np.float32) - want).max() <= TOL16
+    # the fp32-math / fp16-storage fallback kernel is held to the same bound
+    alt = gpu_easu(src, ow, oh, api.FLAG_FORCE_DIRECT)
+    assert np.abs(alt.astype(np.float32) - want).max() <= TOL16
+    for clamp in (0, api.FLAG_RCAS_CLAMP):
+        for sharp in (0.0, 0.25, 2.0):
+            mid = got                                        # RCAS stage on its own: same half input both sides
+            r = gpu_rcas(mid, sharp, clamp)
+            assert api.last_kernel().startswith("rcas_h_packed")
+            wr = ol.rcas(mid.astype(np.float32), ol.rcas_con(sharp), bool(clamp))
+            assert np.abs(r.astype(np.float32) - wr).max() <= TOL16
+            assert np.all(r[..., 3] == 1.0)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "structured"])
+@pytest.mark.parametrize("tag", list(GSIZES))
+def test_against_committed_golden_vectors(kind, tag):
+    """Golden vectors were produced by executing the reference's own source (tests/golden/make_golden.py)."""
+    ow, oh = GSIZES[tag]
+    src = G[kind + "_in_f32"]
+    got = gpu_easu(src, ow, oh, api.FLAG_EXACT)
+    assert np.array_equal(got.view(np.uint32), G["%s_%s_easu_f32" % (kind, tag)].view(np.uint32))
+    src_h = G[kind + "_in_f16"].view(np.float16)
+    got_h = gpu_easu(src_h, ow, oh).astype(np.float32)
+    assert np.abs(got_h - G["%s_%s_easu_f32_of_f16" % (kind, tag)]).max() <= TOL16
+    key = "%s_%s_rcas_s0.25_c0_f32" % (kind, tag)
+    r = gpu_rcas(G["%s_%s_easu_f32" % (kind, tag)], 0.25, api.FLAG_EXACT)
+    assert np.array_equal(r.view(np.uint32), G[key].view(np.uint32))
+
+
+def test_end_to_end_fp16_pipeline_within_1e2():
+    for gen in ("uniform", "structured"):
+        for (iw, ih, ow, oh) in [(192, 108, 384, 216), (192, 108, 288, 162), (192, 108, 250, 141)]:
+            src = F.to_half(getattr(F, gen)(iw, ih, 7))
+            want = ol.rcas(ol.easu(src.astype(np.float32), ow, oh), ol.rcas_con(0.25))
+            flt = F.FSR_Filter()
+            flt.OnCreate()
+            flt.OnCreateWindowSizeDependentResources(iw, ih, ow, oh)
+            out = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+            flt.Upscale(dev(src), out, ow, oh, F.State(renderWidth=iw, renderHeight=ih, rcasAttenuation=0.25))
+            torch.cuda.synchronize()
+            err = np.abs(out.cpu().numpy().astype(np.float32) - want).max()
+            assert err <= TOL16, (gen, iw, ih, ow, oh, err)
+            flt.OnDestroy()
+
+
+def test_flat_frames_and_nan_paths():
+    for v in (0.0, 1.0, 0.5):
+        for dt in (np.float16, np.float32):
+            src = np.full((23, 37, 4), v, dt)
+            e = gpu_easu(src, 74, 46)
+            assert np.all(e[..., :3] == dt(v))
+            for clamp in (0, api.FLAG_RCAS_CLAMP):
+                r = gpu_rcas(e, 0.0, clamp)
+                assert np.isfinite(r.astype(np.float32)).all()
+                w = ol.rcas(e.astype(np.float32), ol.rcas_con(0.0), bool(clamp))
+                assert np.abs(r.astype(np.float32) - w).max() <= (TOL16 if dt == np.float16 else TOL32)
+
+
+def test_padded_pitch_odd_sizes_and_unaligned_fallback():
+    iw, ih, ow, oh = 45, 29, 77, 51
+    src = F.to_half(F.uniform(iw, ih, 11))
+    want = ol.easu(src.astype(np.float32), ow, oh)
+    con = api.easu_con(iw, ih, iw, ih, ow, oh)
+    # padded row pitch (multiple of 16 B): production kernels
+    big_in = torch.zeros((ih, iw + 3, 4), dtype=torch.float16, device="cuda")
+    big_in[:, :iw] = dev(src)
+    big_out = torch.zeros((oh, ow + 5, 4), dtype=torch.float16, device="cuda")
+    api.easu(big_in[:, :iw], big_out[:, :ow], con)
+    assert api.last_kernel().startswith("easu_h_tiled")
+    assert np.abs(big_out[:, :ow].cpu().numpy().astype(np.float32) - want).max() <= TOL16
+    assert torch.all(big_out[:, ow:] == 0)                      # nothing written outside the image
+    # pitch that is only 8-byte aligned: TMA / 128-bit stores impossible -> direct kernels, same answer
+    odd_in = torch.zeros((ih, iw + 2, 4), dtype=torch.float16, device="cuda")[:, 1:iw + 1]
+    odd_in.copy_(dev(src))
+    odd_out = torch.zeros((oh, ow + 2, 4), dtype=torch.float16, device="cuda")[:, 1:ow + 1]
+    api.easu(odd_in, odd_out, con)
+    assert api.last_kernel().startswith("easu_direct<f16io")
+    assert np.abs(odd_out.cpu().numpy().astype(np.float32) - want).max() <= TOL16
+    r_out = torch.zeros_like(odd_out)
+    api.rcas(odd_out, r_out, api.rcas_con(0.25))
+    assert api.last_kernel().startswith("rcas_direct<f16io")
+    wr = ol.rcas(odd_out.cpu().numpy().astype(np.float32), ol.rcas_con(0.25))
+    assert np.abs(r_out.cpu().numpy().astype(np.float32) - wr).max() <= TOL16
+
+
+def test_dynamic_resolution_viewport_and_offset():
+    """viewport != resource size and FsrEasuConOffset (ffx_fsr1.h:161-169, 205-225)."""
+    iw, ih, ow, oh = 80, 60, 96, 72
+    src = F.uniform(iw, ih, 12)
+    for con in (api.easu_con(60, 40, iw, ih, ow, oh), api.easu_con_offset(48, 36, iw, ih, ow, oh, 16.0, 8.0)):
+        want = ol.easu(src, ow, oh, con)
+        got = gpu_easu(src, ow, oh, api.FLAG_EXACT, con=con)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        goth = gpu_easu(F.to_half(src), ow, oh, con=con).astype(np.float32)
+        assert np.abs(goth - ol.easu(F.to_half(src).astype(np.float32), ow, oh, con)).max() <= TOL16
+
+
+@pytest.mark.parametrize("dt", [np.float16, np.float32])
+def test_slabs_compose(dt):
+    """Row windows (the multi-GPU slabs) give exactly the bytes of the whole-frame run."""
+    iw, ih, ow, oh = 64, 60, 128, 120
+    src = F.uniform(iw, ih, 13).astype(dt)
+    tdt = torch.float16 if dt == np.float16 else torch.float32
+    econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
+    full_in = dev(src)
+    tmp = torch.zeros((oh, ow, 4), dtype=tdt, device="cuda")
+    whole = torch.zeros((oh, ow, 4), dtype=tdt, device="cuda")
+    api.upscale(full_in, tmp, whole, econ, rcon)
+    parts = []
+    for world in (3,):
+        plan = F.SlabPlan(ih, oh, world, econ)
+        for r in range(world):
+            n0, n1 = plan.needed_in_rows(r)
+            e0, e1 = plan.easu_rows(r)
+            y0, y1 = plan.out_rows(r)
+            win = full_in[n0:n1].contiguous()
+            t = torch.zeros((e1 - e0, ow, 4), dtype=tdt, device="cuda")
+            o = torch.zeros((y1 - y0, ow, 4), dtype=tdt, device="cuda")
+            api.upscale(api.image(win, height=ih, row0=n0), api.image(t, height=oh, row0=e0),
+                        api.image(o, height=oh, row0=y0), econ, rcon, y0=y0, y1=y1)
+            parts.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(parts), whole)
+
+
+def test_host_frame_entry_point():
+    iw, ih, ow, oh = 120, 68, 240, 136
+    src = F.to_half(F.structured(iw, ih, 14))
+    ctx = api.HostContext(iw, ih, ow, oh, api.FORMAT_RGBA16F)
+    hin = torch.from_numpy(src).pin_memory()
+    hout = torch.zeros((oh, ow, 4), dtype=torch.float16).pin_memory()
+    ctx.upscale_host(hin, hout, 0.25)
+    torch.cuda.synchronize()
+    want = ol.rcas(ol.easu(src.astype(np.float32), ow, oh), ol.rcas_con(0.25))
+    assert np.abs(hout.numpy().astype(np.float32) - want).max() <= TOL16
+    ctx.close()
+
+
+def test_full_size_1080p_to_4k_against_oracle():
+    """BASELINE.json config 2 at full size: every pixel against the oracle (the C oracle does 4K in ~1 s)."""
+    iw, ih, ow, oh = 1920, 1080, 3840, 2160
+    src = F.to_half(F.structured(iw, ih, 2024))
+    din = dev(src)
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    out = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
+    api.upscale(din, tmp, out, econ, rcon)
+    torch.cuda.synchronize()
+    e_want = ol.easu(src.astype(np.float32), ow, oh)
+    e_got = tmp.cpu().numpy()
+    assert np.abs(e_got.astype(np.float32) - e_want).max() <= TOL16
+    r_want = ol.rcas(e_got.astype(np.float32), ol.rcas_con(0.25))
+    assert np.abs(out.cpu().numpy().astype(np.float32) - r_want).max() <= TOL16
+    e2e = ol.rcas(e_want, ol.rcas_con(0.25))
+    assert np.abs(out.cpu().numpy().astype(np.float32) - e2e).max() <= TOL16
+    # size-independent property: the de-ringing clamp — every EASU output lies within the min/max of its 2x2 cell
+    pad = np.pad(src.astype(np.float32), ((2, 2), (2, 2), (0, 0)), mode="edge")
+    ys, xs = np.arange(oh), np.arange(ow)
+    fy = np.floor((ys + 0.5) * 0.5 - 0.5).astype(int) + 2
+    fx = np.floor((xs + 0.5) * 0.5 - 0.5).astype(int) + 2
+    quad = np.stack([pad[fy][:, fx], pad[fy][:, fx + 1], pad[fy + 1][:, fx], pad[fy + 1][:, fx + 1]])
+    g = e_got.astype(np.float32)[..., :3]
+    assert np.all(g >= quad.min(0)[..., :3]) and np.all(g <= quad.max(0)[..., :3])

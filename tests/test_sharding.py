@@ -1,0 +1,82 @@
+"""Row-slab sharding: plan geometry, and the halo exchange on 2 ranks over gloo (CPU).  The per-slab compute
+in these CPU tests is the oracle standing in for the kernels (test infrastructure); the GPU twin is in
+test_gpu_parity.py::test_slabs_compose and bench.py --gpus N."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fsr1_b200 as F
+import oracle_lib as ol
+
+
+@pytest.mark.parametrize("in_h,out_h,world", [(1080, 2160, 8), (2160, 4320, 8), (1440, 2160, 4), (1661, 2160, 3),
+                                               (17, 31, 2), (9, 9, 4), (5, 40, 8)])
+def test_plan_geometry(in_h, out_h, world):
+    econ = ol.easu_con(64, in_h, 128, out_h)
+    plan = F.SlabPlan(in_h, out_h, world, econ)
+    covered = []
+    for r in range(world):
+        y0, y1 = plan.out_rows(r)
+        covered += list(range(y0, y1))
+        n0, n1 = plan.needed_in_rows(r)
+        if y1 > y0:
+            e0, e1 = plan.easu_rows(r)
+            first, last = F.api.easu_input_rows(econ, in_h, e0, e1)
+            assert (n0, n1) == (first, last + 1)      # the plan and the C ABI agree
+        sends, recvs = plan.transfers(r)
+        own = plan.owned_in_rows(r)
+        got = set(range(max(own[0], n0), min(own[1], n1)))
+        for peer, a, b in recvs:
+            assert (r, a, b) in plan.transfers(peer)[0]  # every recv has the matching send
+            got |= set(range(a, b))
+        assert got == set(range(n0, n1))               # owned + received = needed, exactly
+    assert covered == list(range(out_h))
+
+
+def test_cfg5_halo_is_two_rows_each_side():
+    plan = F.SlabPlan(2160, 4320, 8, ol.easu_con(3840, 2160, 7680, 4320))
+    assert plan.needed_in_rows(3) == (808, 1082) and plan.owned_in_rows(3) == (810, 1080)
+    assert plan.halo_bytes(3, 3840, 8) == 2 * 2 * 3840 * 8   # 2 x 61 440 B, SURVEY.md §8(e)
+    assert plan.halo_bytes(0, 3840, 8) == 2 * 3840 * 8
+
+
+def _worker(rank, world, port, shape, tmpdir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    iw, ih, ow, oh = shape
+    frame = F.uniform(iw, ih, 4242)
+    econ, rcon = ol.easu_con(iw, ih, ow, oh), ol.rcas_con(0.25)
+    plan = F.SlabPlan(ih, oh, world, econ)
+    own0, own1 = plan.owned_in_rows(rank)
+    n0, n1 = plan.needed_in_rows(rank)
+    owned = torch.from_numpy(frame[own0:own1].copy())
+    window = torch.full((n1 - n0, iw, 4), float("nan"))
+    F.exchange_halo(plan, rank, owned, window)
+    assert np.array_equal(window.numpy(), frame[n0:n1])          # halo rows arrived where they belong
+    # slab compute (oracle stand-in) on the window placed at its logical rows
+    padded = np.zeros_like(frame)
+    padded[n0:n1] = window.numpy()
+    e0, e1 = plan.easu_rows(rank)
+    y0, y1 = plan.out_rows(rank)
+    tmp = ol.easu(padded, ow, oh, econ, y0=e0, y1=e1)
+    out = ol.rcas(tmp, rcon, False, y0=y0, y1=y1)
+    np.save(os.path.join(tmpdir, "slab%d.npy" % rank), out[y0:y1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,world", [((48, 40, 96, 80), 2), ((40, 33, 52, 43), 2), ((32, 30, 64, 60), 3)])
+def test_halo_exchange_gloo(shape, world, tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, shape, str(tmp_path)), nprocs=world, join=True)
+    iw, ih, ow, oh = shape
+    frame = F.uniform(iw, ih, 4242)
+    want = ol.rcas(ol.easu(frame, ow, oh), ol.rcas_con(0.25), False)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "slab%d.npy" % r)) for r in range(world)])
+    assert np.array_equal(got, want)       # sharded == unsharded, bit for bit
