@@ -1,46 +1,49 @@
-// fsr1_easu_tiled.cu — the production EASU kernel for RGBA16F images on sm_100a.
+// fsr1_easu_tiled.cu — the production EASU kernels for RGBA16F images on sm_100a.
 //
-// One CTA produces a 64x16 tile of the output.  Its input footprint (tile*scale + 3..4 texel halo,
-// the box size is fixed per launch) is fetched by ONE TMA 2D tile load (cp.async.bulk.tensor, elected
-// thread, mbarrier completion) into shared memory; out-of-image parts of the box arrive as zeros and
-// are rewritten to clamp-to-edge (the reference samples through a CLAMP sampler,
-// sample/src/DX12/FSR_Filter.cpp:48-53).  The work is then split the way the arithmetic wants it:
+// Common structure.  A CTA produces a tile of the output.  The tile's input footprint (plus the 4x4
+// tap window's halo) is fetched by ONE TMA 2D tile load (cp.async.bulk.tensor.2d, elected thread,
+// mbarrier complete_tx) into shared memory; parts of the box outside the image arrive as zeros and are
+// rewritten to clamp-to-edge (the reference samples through a CLAMP sampler,
+// sample/src/DX12/FSR_Filter.cpp:48-53).  The arithmetic is then split the way it factors:
 //
-//   phase 1  per INPUT texel   2*luma in fp32                                    (ffx_fsr1.h:363-366)
+//   phase 1  per INPUT texel   2*luma, fp32                                         (ffx_fsr1.h:363-366)
 //   phase 2  per INPUT texel   the FsrEasuSetF terms that do not depend on the output pixel:
-//                              dirX, dirY, lenX+lenY (fp32, F-path bit tricks)      (ffx_fsr1.h:295-313)
-//   phase 3  per OUTPUT pixel  bilinear blend of the 4 nearest texels' terms in fp32 (ffx_fsr1.h:383-386),
-//                              then everything else in packed half2 with TWO horizontally adjacent
-//                              output pixels per lane: normalise / stretch / lobe / clip
-//                              (ffx_fsr1.h:389-409), the 12 taps (ffx_fsr1.h:423-434) and the
-//                              de-ringing clamp (:416-419,437); one 128-bit store per pixel pair.
+//                              dirX, dirY, lenX^2+lenY^2 (fp32, F-path bit tricks)    (ffx_fsr1.h:295-313)
+//   phase 3  per OUTPUT pixel  fp32: bilinear blend of the 4 nearest texels' terms (:383-386), normalise,
+//                              stretch, lobe, clip (:389-409);  packed half2 over TWO output pixels:
+//                              the 12 taps (:423-434) and the de-ringing clamp (:416-419,437).
 //
-// Why fp32 for phases 1-2 and the blend: the edge direction is a normalised difference of lumas; in
-// half precision it is ill-conditioned wherever the gradient nearly cancels, and the result then
-// differs from the fp32 algorithm by up to 0.1 (measured on the CPU model, DESIGN.md "numerics").  With
-// fp32 analysis and half2 taps the kernel stays within 4e-3 of the fp32 oracle (tolerance 1e-2).
-// Hoisting phases 1-2 to once per input texel also removes ~40% of the per-pixel arithmetic at 2x.
+// Precision split (DESIGN.md "numerics"): everything that decides the filter's ORIENTATION is fp32 — in
+// half it is ill-conditioned where gradients nearly cancel and differs from the fp32 algorithm by up to
+// 0.1; the taps (the bulk of the arithmetic) are half2 and stay within ~5e-3 of the fp32 oracle.
+// Pipe split: on B200 HFMA2 issues at half the FFMA rate (one 16-lane sub-pipe), so a kernel that is all
+// half2 is bound by that pipe; keeping the per-pixel set-up in fp32 balances the two FMA sub-pipes.
 //
-// Tap weights use the expanded quadratic form of the rotated/scaled distance
-//   d2(ox,oy) = qa*ox^2 + qb*ox*oy + qc*oy^2,   qa = (dx*l2x)^2+(dy*l2y)^2, qc = (dy*l2x)^2+(dx*l2y)^2,
-//   qb = 2*dx*dy*(l2x^2-l2y^2)
-// so the 12 taps need 2 half2 operations each for d2 instead of 6; the window polynomial
-//   (25/16*(2/5*d2-1)^2 - 9/16) * (lob*d2-1)^2  is evaluated as ((d2/4-5/4)*d2+1) * (lob*d2-1)^2.
+// Tap weights use the expanded quadratic form of the rotated, anisotropically scaled distance
+//   d2(ox,oy) = qa*ox^2 + qb*ox*oy + qc*oy^2,  qa = l2x^2 dx^2 + l2y^2 dy^2,  qc = l2x^2 dy^2 + l2y^2 dx^2,
+//   qb = 2 dx dy (l2x^2 - l2y^2)
+// and the window polynomial (25/16 (2/5 d2 - 1)^2 - 9/16)(lob d2 - 1)^2 = ((d2/4 - 5/4) d2 + 1)(lob d2 - 1)^2.
+//
+// Two kernels:
+//   easu_h_pairs_kernel   any scale; 64x16 output tile per CTA; lane = 2 horizontally adjacent pixels.
+//   easu_h_quad2x_kernel  exactly 2x (con0 = {.5,.5,-.25,-.25}, BASELINE configs[1]): the four output pixels
+//                         (2k+1,2k+2)x(2m+1,2m+2) share one 4x4 window; a lane owns that quad, loads the 12
+//                         taps and the 4 term vectors once, and every tap offset is a compile-time constant.
+//                         Persistent CTAs, TMA double-buffered: tile i+1 loads while tile i computes.
 #include <cuda.h>
 #include "fsr1_common.cuh"
 
 namespace fsr1 {
 
-constexpr int kTileW = 64;  // output pixels per CTA in x
-constexpr int kTileH = 16;  // ... in y
 constexpr int kThreads = 256;
 
 // ---- PTX wrappers: mbarrier + TMA ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -65,60 +68,90 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// ---- half2 helpers ----------------------------------------------------------------------------------
+// ---- small helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 h2c(float v) { return __float2half2_rn(v); }
-// F-path bit tricks applied per lane through fp32 (the H-path magic numbers give a different
-// approximation and break the 1e-2 bound)
-__device__ __forceinline__ __half2 prx_lo_rcp_h2(__half2 a) {
-  const float2 f = __half22float2(a);
-  return __floats2half2_rn(prx_lo_rcp(f.x), prx_lo_rcp(f.y));
-}
-__device__ __forceinline__ __half2 prx_lo_rsq_h2(__half2 a) {
-  const float2 f = __half22float2(a);
-  return __floats2half2_rn(prx_lo_rsq(f.x), prx_lo_rsq(f.y));
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 }
 
-struct PixelTerms { float dx, dy, len; };
-
-// fp32 bilinear blend of the per-texel terms of f,g,j,k (reference order f,g,j,k)
-__device__ __forceinline__ PixelTerms blend_terms(const float4* __restrict__ S, int idx, int stride, float ppx,
-                                                  float ppy) {
-  const float4 f = S[idx], g = S[idx + 1], j = S[idx + stride], k = S[idx + stride + 1];
-  const float ipx = 1.0f - ppx, ipy = 1.0f - ppy;
-  const float wf = ipx * ipy, wg = ppx * ipy, wj = ipx * ppy, wk = ppx * ppy;
-  PixelTerms t;
-  t.dx = fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf)));
-  t.dy = fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf)));
-  t.len = fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf)));
-  return t;
+// Zero-filled out-of-image texels of a TMA box -> clamp-to-edge.  Sources are always in-image positions
+// (never rewritten), destinations always out-of-image ones (never read), so no intermediate barrier.
+__device__ __forceinline__ void clamp_fixup(uint2* tile, int BW, int BH, int gx0, int gy0, int W, int H, int lane,
+                                            int warp) {
+  for (int j = warp; j < BH; j += kThreads / 32) {
+    const int cy = clampi(gy0 + j, 0, H - 1) - gy0;
+    for (int i = lane; i < BW; i += 32) {
+      const int cx = clampi(gx0 + i, 0, W - 1) - gx0;
+      if ((cx != i || cy != j) && cx >= 0 && cx < BW && cy >= 0 && cy < BH) tile[j * BW + i] = tile[cy * BW + cx];
+    }
+  }
 }
 
-// Shared-memory carve-up (dynamic): [tile BH*BW uint2][luma BH*BW float][terms (BH-2)*(BW-2) float4][mbarrier]
-struct Smem {
-  uint2* tile;
-  float* luma;
-  float4* terms;
-  uint64_t* bar;
-};
-__host__ __device__ inline size_t smem_bytes(int BW, int BH) {
-  size_t n = (size_t)BW * BH;
-  size_t off = n * 8;                 // tile, 128B aligned at 0
-  off = (off + 15) & ~(size_t)15;
-  off += n * 4;                       // luma
-  off = (off + 15) & ~(size_t)15;
-  off += (size_t)(BW - 2) * (BH - 2) * 16;  // terms
-  off = (off + 15) & ~(size_t)15;
-  off += 16;                          // barrier
-  return off + 128;                   // slack for manual 128B alignment of the base
+__device__ __forceinline__ float texel_luma(uint2 t) {  // 2*luma = 0.5 B + (0.5 R + G); exact in fp32
+  const float2 rg = __half22float2(u2h2(t.x));
+  return fmaf(__low2float(u2h2(t.y)), 0.5f, fmaf(rg.x, 0.5f, rg.y));
+}
+
+// FsrEasuSetF without the bilinear weight: (dirX, dirY, lenX^2 + lenY^2) of the texel whose luma is lC.
+__device__ __forceinline__ float4 texel_terms(float lA, float lB, float lC, float lD, float lE) {
+  const float dirX = lD - lB, dirY = lE - lA;
+  const float lenX = sat(fabsf(dirX) * prx_lo_rcp(fmaxf(fabsf(lD - lC), fabsf(lC - lB))));
+  const float lenY = sat(fabsf(dirY) * prx_lo_rcp(fmaxf(fabsf(lE - lC), fabsf(lC - lA))));
+  return make_float4(dirX, dirY, fmaf(lenX, lenX, lenY * lenY), 0.0f);
+}
+
+// Per-pixel filter shape from the blended (dir, len): the coefficients the tap loop needs.  fp32.
+struct Shape { float qa, qb, qc, lob, clp; };
+__device__ __forceinline__ Shape pixel_shape(float dx, float dy, float len) {
+  const float dirR = fmaf(dx, dx, dy * dy);
+  const bool zro = dirR < (1.0f / 32768.0f);
+  const float rs = zro ? 1.0f : prx_lo_rsq(dirR);
+  dx = (zro ? 1.0f : dx) * rs;
+  dy *= rs;
+  len *= 0.5f;
+  len *= len;
+  const float dx2 = dx * dx, dy2 = dy * dy;
+  const float stretch = (dx2 + dy2) * prx_lo_rcp(fmaxf(fabsf(dx), fabsf(dy)));
+  const float l2x = fmaf(stretch - 1.0f, len, 1.0f), l2y = fmaf(-0.5f, len, 1.0f);
+  Shape s;
+  s.lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
+  s.clp = prx_lo_rcp(s.lob);
+  const float X2 = l2x * l2x, Y2 = l2y * l2y;
+  s.qa = fmaf(X2, dx2, Y2 * dy2);
+  s.qc = fmaf(X2, dy2, Y2 * dx2);
+  s.qb = (dx * dy * 2.0f) * (X2 - Y2);
+  return s;
+}
+
+// window weight of (up to) two pixels at squared distance d2
+__device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 clp) {
+  d2 = __hmin2(d2, clp);
+  const __half2 wb = __hfma2(__hfma2(h2c(0.25f), d2, h2c(-1.25f)), d2, h2c(1.0f));
+  __half2 wa = __hfma2(lob, d2, h2c(-1.0f));
+  wa = __hmul2(wa, wa);
+  return __hmul2(wb, wa);
+}
+
+// =======================================================================================================
+//  generic kernel: any scale, lane = pixel pair (2*lane, 2*lane+1), rows warp and warp+8 of a 64x16 tile
+// =======================================================================================================
+constexpr int kTileW = 64, kTileH = 16;
+
+__host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
+  size_t n = (size_t)BW * BH, off = (n * 8 + 15) & ~(size_t)15;
+  off = (off + n * 4 + 15) & ~(size_t)15;
+  off = (off + (size_t)(BW - 2) * (BH - 2) * 16 + 15) & ~(size_t)15;
+  return off + 16 + 128;  // + barrier + slack for the manual 128B alignment
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH) {
+easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH) {
   extern __shared__ unsigned char smem_raw[];
-  // 128-byte align the carve-up by OFFSET (pointer arithmetic on the shared array keeps the
-  // address space, so the accesses below compile to LDS/STS, not generic LD/ST)
+  // 128-byte align by OFFSET (pointer arithmetic on the shared array keeps the address space -> LDS/STS)
   unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int n = BW * BH;
   uint2* tile = reinterpret_cast<uint2*>(base);
@@ -135,11 +168,12 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
   float dummy;
   easu_pos(ox0, p.c0x, p.c0z, fx0, dummy);
   easu_pos(oy0, p.c0y, p.c0w, fy0, dummy);
-  fx0 -= 1;  // box origin = first tap column/row of the tile's first pixel
-  fy0 -= 1;
+  fx0 = (fx0 - 1) & ~1;  // box origin = first tap column/row of the tile's first pixel; the column is rounded
+  fy0 -= 1;              // down to even: TMA traps unless the box starts on a 16-byte boundary (2 texels)
 
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_fence_init();
   }
   __syncthreads();
   if (tid == 0) {
@@ -148,44 +182,29 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
   }
   mbar_wait(bar, 0);
 
-  // clamp-to-edge fix-up of the zero-filled out-of-image part of the box (border tiles only)
-  const bool border = fx0 < 0 || fy0 < 0 || fx0 + BW > p.in.w || fy0 + BH > p.in.h;
-  if (border) {
-    for (int j = warp; j < BH; j += kThreads / 32) {
-      const int gy = fy0 + j, cy = clampi(gy, 0, p.in.h - 1) - fy0;
-      for (int i = lane; i < BW; i += 32) {
-        const int gx = fx0 + i, cx = clampi(gx, 0, p.in.w - 1) - fx0;
-        if ((cx != i || cy != j) && cx >= 0 && cx < BW && cy >= 0 && cy < BH) tile[j * BW + i] = tile[cy * BW + cx];
-      }
-    }
+  if (fx0 < 0 || fy0 < 0 || fx0 + BW > p.in.w || fy0 + BH > p.in.h) {  // border tiles only (CTA-uniform)
+    clamp_fixup(tile, BW, BH, fx0, fy0, p.in.w, p.in.h, lane, warp);
     __syncthreads();
   }
 
-  // phase 1: 2*luma per texel, fp32 (exact: inputs are halves)
-  for (int i = tid; i < n; i += kThreads) {
-    const uint2 t = tile[i];
-    const float2 rg = __half22float2(u2h2(t.x));
-    const float b = __low2float(u2h2(t.y));
-    L[i] = fmaf(b, 0.5f, fmaf(rg.x, 0.5f, rg.y));
-  }
+  for (int i = tid; i < n; i += kThreads) L[i] = texel_luma(tile[i]);  // phase 1
   __syncthreads();
 
-  // phase 2: per-texel direction / length terms for the inner texels (those that can be f,g,j,k)
-  const int SW = BW - 2;
-  for (int j = 1 + warp; j < BH - 1; j += kThreads / 32) {
-    for (int i = 1 + lane; i < BW - 1; i += 32) {
-      const float lC = L[j * BW + i], lB = L[j * BW + i - 1], lD = L[j * BW + i + 1];
-      const float lA = L[(j - 1) * BW + i], lE = L[(j + 1) * BW + i];
-      const float dirX = lD - lB, dirY = lE - lA;
-      float lenX = sat(fabsf(dirX) * prx_lo_rcp(fmaxf(fabsf(lD - lC), fabsf(lC - lB))));
-      float lenY = sat(fabsf(dirY) * prx_lo_rcp(fmaxf(fabsf(lE - lC), fabsf(lC - lA))));
-      S[(j - 1) * SW + (i - 1)] = make_float4(dirX, dirY, fmaf(lenX, lenX, lenY * lenY), 0.0f);
+  // phase 2 over the (BW-2)x(BH-2) inner texels, flattened so that all lanes stay busy
+  const int SW = BW - 2, nS = SW * (BH - 2);
+  {
+    int j = tid / SW, i = tid - j * SW;
+    const int dj = kThreads / SW, di = kThreads - dj * SW;
+    for (int idx = tid; idx < nS; idx += kThreads) {
+      const float* c = L + (j + 1) * BW + (i + 1);
+      S[idx] = texel_terms(c[-BW], c[-1], c[0], c[1], c[BW]);
+      i += di; j += dj;
+      if (i >= SW) { i -= SW; j += 1; }
     }
   }
   __syncthreads();
 
-  // phase 3: two pixel pairs per thread: columns (2*lane, 2*lane+1), rows warp and warp+8
-  const __half2 kZero = h2c(0.0f), kOne = h2c(1.0f);
+  // phase 3
 #pragma unroll 1
   for (int pr = 0; pr < kTileH / 8; pr++) {
     const int ox = ox0 + lane * 2, oy = oy0 + warp + pr * 8;
@@ -196,34 +215,29 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
     easu_pos(ox + 1 < p.out.w ? ox + 1 : ox, p.c0x, p.c0z, fxB, ppxB);  // odd width: B duplicates A
     easu_pos(oy, p.c0y, p.c0w, fy, ppy);
     const int cy = fy - fy0, cxA = fxA - fx0, cxB = fxB - fx0;  // >= 1 by construction
-    const PixelTerms tA = blend_terms(S, (cy - 1) * SW + (cxA - 1), SW, ppxA, ppy);
-    const PixelTerms tB = blend_terms(S, (cy - 1) * SW + (cxB - 1), SW, ppxB, ppy);
 
-    // ---- per-pixel kernel shape, packed (A,B) ----
-    __half2 dx = __floats2half2_rn(tA.dx, tB.dx), dy = __floats2half2_rn(tA.dy, tB.dy);
-    __half2 len = __floats2half2_rn(tA.len, tB.len);
-    __half2 dirR = __hfma2(dx, dx, __hmul2(dy, dy));
-    const uint32_t zro = __hlt2_mask(dirR, h2c(1.0f / 32768.0f));
-    __half2 rs = prx_lo_rsq_h2(dirR);
-    rs = u2h2((h22u(rs) & ~zro) | (h22u(kOne) & zro));
-    dx = u2h2((h22u(dx) & ~zro) | (h22u(kOne) & zro));
-    dx = __hmul2(dx, rs);
-    dy = __hmul2(dy, rs);
-    len = __hmul2(len, h2c(0.5f));
-    len = __hmul2(len, len);
-    const __half2 dx2 = __hmul2(dx, dx), dy2 = __hmul2(dy, dy);
-    const __half2 stretch =
-        __hmul2(__hadd2(dx2, dy2), prx_lo_rcp_h2(__hmax2(__habs2(dx), __habs2(dy))));
-    const __half2 l2x = __hfma2(__hsub2(stretch, kOne), len, kOne);
-    const __half2 l2y = __hfma2(h2c(-0.5f), len, kOne);
-    const __half2 lob = __hfma2(h2c((float)((1.0 / 4.0 - 0.04) - 0.5)), len, h2c(0.5f));
-    const __half2 clp = prx_lo_rcp_h2(lob);
-    const __half2 X2 = __hmul2(l2x, l2x), Y2 = __hmul2(l2y, l2y);
-    const __half2 qa = __hfma2(X2, dx2, __hmul2(Y2, dy2));
-    const __half2 qc = __hfma2(X2, dy2, __hmul2(Y2, dx2));
-    const __half2 qb = __hmul2(__hmul2(__hadd2(dx, dx), dy), __hsub2(X2, Y2));
+    // fp32: blend of the f,g,j,k terms and the filter shape, per pixel
+    Shape sA, sB;
+    {
+      const float ipy = 1.0f - ppy;
+      const float4* q = S + (cy - 1) * SW + (cxA - 1);
+      float4 f = q[0], g = q[1], j = q[SW], k = q[SW + 1];
+      float ipx = 1.0f - ppxA, wf = ipx * ipy, wg = ppxA * ipy, wj = ipx * ppy, wk = ppxA * ppy;
+      sA = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))),
+                       fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
+                       fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
+      q = S + (cy - 1) * SW + (cxB - 1);
+      f = q[0]; g = q[1]; j = q[SW]; k = q[SW + 1];
+      ipx = 1.0f - ppxB; wf = ipx * ipy; wg = ppxB * ipy; wj = ipx * ppy; wk = ppxB * ppy;
+      sB = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))),
+                       fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
+                       fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
+    }
+    const __half2 qa = __floats2half2_rn(sA.qa, sB.qa), qb = __floats2half2_rn(sA.qb, sB.qb);
+    const __half2 qc = __floats2half2_rn(sA.qc, sB.qc), lob = __floats2half2_rn(sA.lob, sB.lob);
+    const __half2 clp = __floats2half2_rn(sA.clp, sB.clp);
 
-    // per-column / per-row pieces of d2:  d2(k,r) = PX[k] + QY[r] + SB[k]*oy[r]
+    // per-column / per-row pieces of d2:  d2(k,r) = PX[k] + QY[r] + SB[k]*OY[r]
     const __half2 ppx2 = __floats2half2_rn(ppxA, ppxB), ppy2 = __float2half2_rn(ppy);
     __half2 PX[4], SB[4], QY[4], OY[4];
 #pragma unroll
@@ -237,19 +251,14 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
 
     const uint2* tA0 = tile + (cy - 1) * BW + (cxA - 1);
     const uint2* tB0 = tile + (cy - 1) * BW + (cxB - 1);
+    const __half2 kZero = h2c(0.0f);
     __half2 aRG_A = kZero, aBA_A = kZero, aRG_B = kZero, aBA_B = kZero, aW = kZero;
     __half2 mnRG_A, mnBA_A, mxRG_A, mxBA_A, mnRG_B, mnBA_B, mxRG_B, mxBA_B;
-    const __half2 c025 = h2c(0.25f), cm125 = h2c(-1.25f), cm1 = h2c(-1.0f);
 
 #define FSR1_TAP(R, K)                                                                             \
     {                                                                                              \
       const uint2 ca = tA0[(R) * BW + (K)], cb = tB0[(R) * BW + (K)];                              \
-      __half2 d2 = __hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R]));                                   \
-      d2 = __hmin2(d2, clp);                                                                       \
-      const __half2 wb = __hfma2(__hfma2(c025, d2, cm125), d2, kOne);                              \
-      __half2 wa = __hfma2(lob, d2, cm1);                                                          \
-      wa = __hmul2(wa, wa);                                                                        \
-      const __half2 w = __hmul2(wb, wa);                                                           \
+      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);        \
       const __half2 wA2 = __low2half2(w), wB2 = __high2half2(w);                                   \
       aRG_A = __hfma2(u2h2(ca.x), wA2, aRG_A);                                                     \
       aBA_A = __hfma2(u2h2(ca.y), wA2, aBA_A);                                                     \
@@ -274,7 +283,7 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
 #undef FSR1_TAP
 
     const float2 aWf = __half22float2(aW);
-    const __half2 rA = __float2half2_rn(__frcp_rn(aWf.x)), rB = __float2half2_rn(__frcp_rn(aWf.y));
+    const __half2 rA = __float2half2_rn(rcp_approx(aWf.x)), rB = __float2half2_rn(rcp_approx(aWf.y));
     __half2 oRG_A = __hmin2(mxRG_A, __hmax2(mnRG_A, __hmul2(aRG_A, rA)));
     __half2 oBA_A = __hmin2(mxBA_A, __hmax2(mnBA_A, __hmul2(aBA_A, rA)));
     __half2 oRG_B = __hmin2(mxRG_B, __hmax2(mnRG_B, __hmul2(aRG_B, rB)));
@@ -287,6 +296,156 @@ easu_h_tiled_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
     } else {
       *reinterpret_cast<uint2*>(orow + (size_t)ox * 8) = make_uint2(h22u(oRG_A), h22u(oBA_A));
     }
+  }
+}
+
+// =======================================================================================================
+//  2x kernel: lane = the quad of output pixels sharing input cell (k,m); persistent, double-buffered TMA
+// =======================================================================================================
+constexpr int kQCX = 32, kQCY = 16;              // cells per tile (= 64 x 32 output pixels)
+constexpr int kQBW = kQCX + 4, kQBH = kQCY + 3;  // TMA box: 36 x 19 texels (35 needed, even width)
+constexpr int kQSW = kQBW - 2, kQSH = kQBH - 2;  // inner texels carrying terms: 34 x 17
+constexpr int kQTileElems = kQBW * kQBH;
+constexpr int kQTilePad = ((kQTileElems * 8 + 127) / 128) * 128 / 8;  // buffer stride, keeps 128B alignment
+
+// One pixel pair (A: px=.25, B: px=.75) of the quad; kBottom selects py=.75.  t = the 12 taps (RG,BA);
+// every tap offset is a constant, so d2 is three half2 FMAs against immediates.
+template <bool kBottom>
+__device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& sA, const Shape& sB, __half2 mnR,
+                                          __half2 mnG, __half2 mnB, __half2 mxR, __half2 mxG, __half2 mxB,
+                                          uint2& outA, uint2& outB) {
+  const __half2 qa = __floats2half2_rn(sA.qa, sB.qa), qb = __floats2half2_rn(sA.qb, sB.qb);
+  const __half2 qc = __floats2half2_rn(sA.qc, sB.qc), lob = __floats2half2_rn(sA.lob, sB.lob);
+  const __half2 clp = __floats2half2_rn(sA.clp, sB.clp);
+  const __half2 kZero = h2c(0.0f);
+  __half2 aR = kZero, aG = kZero, aB = kZero, aW = kZero;
+  constexpr float py = kBottom ? 0.75f : 0.25f;
+#define FSR1_QTAP(R, K)                                                                                     \
+  {                                                                                                         \
+    constexpr float oxA = (float)((K)-1) - 0.25f, oxB = (float)((K)-1) - 0.75f, oy = (float)((R)-1) - py;     \
+    const __half2 d2 = __hfma2(qa, __floats2half2_rn(oxA * oxA, oxB * oxB),                                  \
+                               __hfma2(qc, __floats2half2_rn(oy * oy, oy * oy),                              \
+                                       __hmul2(qb, __floats2half2_rn(oxA * oy, oxB * oy))));                 \
+    const __half2 w = tap_weight(d2, lob, clp);                                                             \
+    const __half2 rg = u2h2(t[R][K].x), ba = u2h2(t[R][K].y);                                               \
+    aR = __hfma2(__low2half2(rg), w, aR);                                                                   \
+    aG = __hfma2(__high2half2(rg), w, aG);                                                                  \
+    aB = __hfma2(__low2half2(ba), w, aB);                                                                   \
+    aW = __hadd2(aW, w);                                                                                    \
+  }
+  FSR1_QTAP(1, 1) FSR1_QTAP(1, 2) FSR1_QTAP(2, 1) FSR1_QTAP(2, 2)
+  FSR1_QTAP(0, 1) FSR1_QTAP(0, 2) FSR1_QTAP(1, 0) FSR1_QTAP(1, 3)
+  FSR1_QTAP(2, 0) FSR1_QTAP(2, 3) FSR1_QTAP(3, 1) FSR1_QTAP(3, 2)
+#undef FSR1_QTAP
+  const float2 aWf = __half22float2(aW);
+  const __half2 r = __floats2half2_rn(rcp_approx(aWf.x), rcp_approx(aWf.y));
+  const __half2 oR = __hmin2(mxR, __hmax2(mnR, __hmul2(aR, r)));
+  const __half2 oG = __hmin2(mxG, __hmax2(mnG, __hmul2(aG, r)));
+  const __half2 oB = __hmin2(mxB, __hmax2(mnB, __hmul2(aB, r)));
+  const __half2 one = h2c(1.0f);
+  outA = make_uint2(h22u(__lows2half2(oR, oG)), h22u(__lows2half2(oB, one)));
+  outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
+}
+
+struct __align__(128) QuadSmem {
+  uint2 tile[2][kQTilePad];
+  float4 S[kQSW * kQSH];
+  float L[kQTileElems];
+  uint64_t bar[2];
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
+                     const int n_tiles, const int mbase) {
+  __shared__ QuadSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // tile t: cells k in [32 tx - 1, +32), m in [mbase + 16 ty, +16); box origin = (first cell) - 1
+  auto box_x = [&](int t) { return (t % tiles_x) * kQCX - 2; };
+  auto box_y = [&](int t) { return mbase + (t / tiles_x) * kQCY - 1; };
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tiles) {
+    mbar_expect_tx(&sm.bar[0], kQTileElems * 8u);
+    tma_load_2d(sm.tile[0], &tmap, box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
+  }
+  for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
+    const int b = it & 1;
+    const int tn = t + gridDim.x;
+    if (tid == 0 && tn < n_tiles) {  // prefetch the next tile into the other buffer (its readers all passed
+      fence_proxy_async();           // the barrier that closed the previous iteration)
+      mbar_expect_tx(&sm.bar[b ^ 1], kQTileElems * 8u);
+      tma_load_2d(sm.tile[b ^ 1], &tmap, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
+    }
+    uint2* tile = sm.tile[b];
+    const int gx0 = box_x(t), gy0 = box_y(t);
+    mbar_wait(&sm.bar[b], (it >> 1) & 1);
+    if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + kQBH > p.in.h) {
+      clamp_fixup(tile, kQBW, kQBH, gx0, gy0, p.in.w, p.in.h, lane, warp);
+      fence_proxy_async();  // these generic-proxy writes are later overwritten by a TMA (async proxy) load
+      __syncthreads();
+    }
+    for (int i = tid; i < kQTileElems; i += kThreads) sm.L[i] = texel_luma(tile[i]);
+    __syncthreads();
+    for (int idx = tid; idx < kQSW * kQSH; idx += kThreads) {
+      const int j = idx / kQSW, i = idx - j * kQSW;
+      const float* c = sm.L + (j + 1) * kQBW + (i + 1);
+      sm.S[idx] = texel_terms(c[-kQBW], c[-1], c[0], c[1], c[kQBW]);
+    }
+    __syncthreads();
+
+    const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
+#pragma unroll 1
+    for (int q = 0; q < kQCY / 8; q++) {
+      const int r = warp + q * 8;                // cell row within the tile
+      const int oyT = (gy0 + 1 + r) * 2 + 1;     // output rows 2m+1 (top pair), 2m+2 (bottom pair)
+      const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
+      if (oxA >= p.out.w || !(rowT || rowB)) continue;
+      uint2 tp[4][4];
+      const uint2* t0 = tile + r * kQBW + lane;
+#pragma unroll
+      for (int R = 0; R < 4; R++)
+#pragma unroll
+        for (int K = 0; K < 4; K++)
+          if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kQBW + K];
+      const float4* s0 = sm.S + r * kQSW + lane;
+      const float4 f = s0[0], g = s0[1], j = s0[kQSW], k = s0[kQSW + 1];
+      // de-ringing bounds of the quad: min/max of f,g,j,k per channel, broadcast to both lanes
+      const __half2 mnRG = __hmin2(__hmin2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmin2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
+      const __half2 mxRG = __hmax2(__hmax2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmax2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
+      const __half2 mnBA = __hmin2(__hmin2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmin2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
+      const __half2 mxBA = __hmax2(__hmax2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmax2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
+      const __half2 mnR = __low2half2(mnRG), mnG = __high2half2(mnRG), mnB = __low2half2(mnBA);
+      const __half2 mxR = __low2half2(mxRG), mxG = __high2half2(mxRG), mxB = __low2half2(mxBA);
+      // bilinear blends with the four constant weight sets (pp = .25/.75): horizontal first
+      const float fx = 0.75f, gx = 0.25f;
+      const float3 t25 = make_float3(fmaf(g.x, gx, f.x * fx), fmaf(g.y, gx, f.y * fx), fmaf(g.z, gx, f.z * fx));
+      const float3 t75 = make_float3(fmaf(g.x, fx, f.x * gx), fmaf(g.y, fx, f.y * gx), fmaf(g.z, fx, f.z * gx));
+      const float3 b25 = make_float3(fmaf(k.x, gx, j.x * fx), fmaf(k.y, gx, j.y * fx), fmaf(k.z, gx, j.z * fx));
+      const float3 b75 = make_float3(fmaf(k.x, fx, j.x * gx), fmaf(k.y, fx, j.y * gx), fmaf(k.z, fx, j.z * gx));
+      unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
+      const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
+      uint2 oA, oB;
+      if (rowT) {
+        const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
+        const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
+        quad_pair<false>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+        if (okA) *reinterpret_cast<uint2*>(orow) = oA;
+        if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
+      }
+      if (rowB) {
+        const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
+        const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
+        quad_pair<true>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+        if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
+        if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
+      }
+    }
+    __syncthreads();  // L, S and this tile buffer are free again
   }
 }
 
@@ -309,6 +468,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// one RGBA16F texel = one 64-bit TMA element; tensor = the stored window of the image
+static bool make_tmap(CUtensorMap* tmap, const ImgView& in, int BW, int BH) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)in.w, (cuuint64_t)in.rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)in.pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)BW, (cuuint32_t)BH};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Same float arithmetic as easu_pos on the device.
 static inline int host_fp(int o, float scale, float offset) {
   volatile float m = (float)o * scale;
@@ -316,51 +488,65 @@ static inline int host_fp(int o, float scale, float offset) {
   return (int)floorf(s);
 }
 
-// Largest footprint (in texels) any tile of `tile` output pixels needs along one axis.
-static int max_footprint(int n_out, int first, int tile, float scale, float offset) {
+// Largest footprint (in texels) any tile of `tile` output pixels needs along one axis; with even_origin the
+// box starts at the even texel at or before the first tap (see the kernel).
+static int max_footprint(int n_out, int first, int tile, float scale, float offset, bool even_origin) {
   int best = 4;
   for (int o0 = first; o0 < n_out; o0 += tile) {
     const int o1 = (o0 + tile - 1 < n_out - 1) ? o0 + tile - 1 : n_out - 1;
-    const int span = host_fp(o1, scale, offset) - host_fp(o0, scale, offset) + 4;
+    int origin = host_fp(o0, scale, offset) - 1;
+    if (even_origin) origin &= ~1;
+    const int span = host_fp(o1, scale, offset) + 2 - origin + 1;
     if (span > best) best = span;
   }
   return best;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name) {
-  // layout requirements of TMA and of the 128-bit stores
+  // layout requirements of TMA and of the vector stores
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) return cudaErrorNotSupported;
-  int BW = max_footprint(p.out.w, 0, kTileW, p.c0x, p.c0z);
-  int BH = max_footprint(p.y1, p.y0, kTileH, p.c0y, p.c0w);
+  CUtensorMap tmap;
+
+  if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
+    if (!make_tmap(&tmap, p.in, kQBW, kQBH)) return cudaErrorNotSupported;
+    const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
+    const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
+    const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX, tiles_y = (m_last - m_first + 1 + kQCY - 1) / kQCY;
+    const int n_tiles = tiles_x * tiles_y;
+    const int grid = n_tiles < 2 * sm_count() ? n_tiles : 2 * sm_count();
+    easu_h_quad2x_kernel<<<grid, kThreads, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+    *name = "easu_h_quad2x<persistent,tma2>";
+    return cudaGetLastError();
+  }
+
+  int BW = max_footprint(p.out.w, 0, kTileW, p.c0x, p.c0z, true);
+  int BH = max_footprint(p.y1, p.y0, kTileH, p.c0y, p.c0w, false);
   BW = (BW + 1) & ~1;  // inner box extent must be a multiple of 16 bytes
   if (BW > 256 || BH > 256) return cudaErrorNotSupported;
-  const size_t smem = smem_bytes(BW, BH);
+  const size_t smem = pairs_smem_bytes(BW, BH);
   if (smem > 200 * 1024) return cudaErrorNotSupported;
-
-  CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)p.in.pitch};
-  const cuuint32_t box[2] = {(cuuint32_t)BW, (cuuint32_t)BH};
-  const cuuint32_t estr[2] = {1, 1};
-  // one RGBA16F texel = one 64-bit element
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, p.in.base, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
-
+  if (!make_tmap(&tmap, p.in, BW, BH)) return cudaErrorNotSupported;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(easu_h_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(easu_h_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   const dim3 grid((p.out.w + kTileW - 1) / kTileW, (p.y1 - p.y0 + kTileH - 1) / kTileH, 1);
-  easu_h_tiled_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH);
-  *name = "easu_h_tiled<64x16,tma>";
+  easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH);
+  *name = "easu_h_pairs<64x16,tma>";
   return cudaGetLastError();
 }
 
