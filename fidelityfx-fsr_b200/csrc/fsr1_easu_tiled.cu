@@ -31,6 +31,7 @@
 //                         taps and the 4 term vectors once, and every tap offset is a compile-time constant.
 //                         Persistent CTAs, TMA double-buffered: tile i+1 loads while tile i computes.
 #include <cuda.h>
+#include <stdlib.h>
 #include "fsr1_common.cuh"
 
 namespace fsr1 {
@@ -148,7 +149,7 @@ __host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
   return off + 16 + 128;  // + barrier + slack for the manual 128B alignment
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte align by OFFSET (pointer arithmetic on the shared array keeps the address space -> LDS/STS)
@@ -302,11 +303,14 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
 // =======================================================================================================
 //  2x kernel: lane = the quad of output pixels sharing input cell (k,m); persistent, double-buffered TMA
 // =======================================================================================================
-constexpr int kQCX = 32, kQCY = 16;              // cells per tile (= 64 x 32 output pixels)
-constexpr int kQBW = kQCX + 4, kQBH = kQCY + 3;  // TMA box: 36 x 19 texels (35 needed, even width)
-constexpr int kQSW = kQBW - 2, kQSH = kQBH - 2;  // inner texels carrying terms: 34 x 17
-constexpr int kQTileElems = kQBW * kQBH;
-constexpr int kQTilePad = ((kQTileElems * 8 + 127) / 128) * 128 / 8;  // buffer stride, keeps 128B alignment
+constexpr int kQCX = 32;        // cells per tile in x (= 64 output pixels); one lane per cell
+constexpr int kQBW = kQCX + 4;  // TMA box width: 36 texels (35 needed, even width)
+constexpr int kQSW = kQBW - 2;  // inner texels carrying terms: 34 per row
+// NW warps per CTA, each warp owns 2 cell rows: cells per tile 32 x 2NW, box 36 x (2NW+3), terms 34 x (2NW+1)
+template <int NW> struct QuadCfg {
+  static constexpr int kCY = 2 * NW, kBH = kCY + 3, kSH = kBH - 2, kElems = kQBW * kBH;
+  static constexpr int kPad = ((kElems * 8 + 127) / 128) * 128 / 8;  // buffer stride keeping 128B alignment
+};
 
 // One pixel pair (A: px=.25, B: px=.75) of the quad; kBottom selects py=.75.  t = the 12 taps (RG,BA);
 // every tap offset is a constant, so d2 is three half2 FMAs against immediates.
@@ -347,17 +351,20 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
   outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
 }
 
-struct __align__(128) QuadSmem {
-  uint2 tile[2][kQTilePad];
-  float4 S[kQSW * kQSH];
-  float L[kQTileElems];
+template <int NW> struct __align__(128) QuadSmem {
+  uint2 tile[2][QuadCfg<NW>::kPad];
+  float4 S[kQSW * QuadCfg<NW>::kSH];
+  float L[QuadCfg<NW>::kElems];
   uint64_t bar[2];
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
                      const int n_tiles, const int mbase) {
-  __shared__ QuadSmem sm;
+  using C = QuadCfg<NW>;
+  constexpr int NT = NW * 32;
+  __shared__ QuadSmem<NW> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -365,12 +372,12 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     mbar_fence_init();
   }
   __syncthreads();
-  // tile t: cells k in [32 tx - 1, +32), m in [mbase + 16 ty, +16); box origin = (first cell) - 1
+  // tile t: cells k in [32 tx - 1, +32), m in [mbase + kCY ty, +kCY); box origin = (first cell) - 1
   auto box_x = [&](int t) { return (t % tiles_x) * kQCX - 2; };
-  auto box_y = [&](int t) { return mbase + (t / tiles_x) * kQCY - 1; };
+  auto box_y = [&](int t) { return mbase + (t / tiles_x) * C::kCY - 1; };
   int t = blockIdx.x;
   if (tid == 0 && t < n_tiles) {
-    mbar_expect_tx(&sm.bar[0], kQTileElems * 8u);
+    mbar_expect_tx(&sm.bar[0], C::kElems * 8u);
     tma_load_2d(sm.tile[0], &tmap, box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
   }
   for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
@@ -378,20 +385,26 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     const int tn = t + gridDim.x;
     if (tid == 0 && tn < n_tiles) {  // prefetch the next tile into the other buffer (its readers all passed
       fence_proxy_async();           // the barrier that closed the previous iteration)
-      mbar_expect_tx(&sm.bar[b ^ 1], kQTileElems * 8u);
+      mbar_expect_tx(&sm.bar[b ^ 1], C::kElems * 8u);
       tma_load_2d(sm.tile[b ^ 1], &tmap, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
     }
     uint2* tile = sm.tile[b];
     const int gx0 = box_x(t), gy0 = box_y(t);
     mbar_wait(&sm.bar[b], (it >> 1) & 1);
-    if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + kQBH > p.in.h) {
-      clamp_fixup(tile, kQBW, kQBH, gx0, gy0, p.in.w, p.in.h, lane, warp);
+    if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + C::kBH > p.in.h) {
+      for (int j = warp; j < C::kBH; j += NW) {
+        const int cy = clampi(gy0 + j, 0, p.in.h - 1) - gy0;
+        for (int i = lane; i < kQBW; i += 32) {
+          const int cx = clampi(gx0 + i, 0, p.in.w - 1) - gx0;
+          if ((cx != i || cy != j) && cx >= 0 && cx < kQBW && cy >= 0 && cy < C::kBH) tile[j * kQBW + i] = tile[cy * kQBW + cx];
+        }
+      }
       fence_proxy_async();  // these generic-proxy writes are later overwritten by a TMA (async proxy) load
       __syncthreads();
     }
-    for (int i = tid; i < kQTileElems; i += kThreads) sm.L[i] = texel_luma(tile[i]);
+    for (int i = tid; i < C::kElems; i += NT) sm.L[i] = texel_luma(tile[i]);
     __syncthreads();
-    for (int idx = tid; idx < kQSW * kQSH; idx += kThreads) {
+    for (int idx = tid; idx < kQSW * C::kSH; idx += NT) {
       const int j = idx / kQSW, i = idx - j * kQSW;
       const float* c = sm.L + (j + 1) * kQBW + (i + 1);
       sm.S[idx] = texel_terms(c[-kQBW], c[-1], c[0], c[1], c[kQBW]);
@@ -400,8 +413,8 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
 
     const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
 #pragma unroll 1
-    for (int q = 0; q < kQCY / 8; q++) {
-      const int r = warp + q * 8;                // cell row within the tile
+    for (int q = 0; q < 2; q++) {
+      const int r = warp + q * NW;               // cell row within the tile
       const int oyT = (gy0 + 1 + r) * 2 + 1;     // output rows 2m+1 (top pair), 2m+2 (bottom pair)
       const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
       if (oxA >= p.out.w || !(rowT || rowB)) continue;
@@ -520,15 +533,23 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   CUtensorMap tmap;
 
   if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
-    if (!make_tmap(&tmap, p.in, kQBW, kQBH)) return cudaErrorNotSupported;
+    static int variant = -1;  // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6)
+    if (variant < 0) { const char* e = getenv("FSR1_EASU_QUAD_VARIANT"); variant = e ? atoi(e) : 2; }
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
-    const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX, tiles_y = (m_last - m_first + 1 + kQCY - 1) / kQCY;
-    const int n_tiles = tiles_x * tiles_y;
-    const int grid = n_tiles < 2 * sm_count() ? n_tiles : 2 * sm_count();
-    easu_h_quad2x_kernel<<<grid, kThreads, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
-    *name = "easu_h_quad2x<persistent,tma2>";
-    return cudaGetLastError();
+    const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
+    auto launch = [&](auto kernel, int nw, int per_sm, const char* nm) -> cudaError_t {
+      const int cy = 2 * nw;
+      if (!make_tmap(&tmap, p.in, kQBW, cy + 3)) return cudaErrorNotSupported;
+      const int tiles_y = (m_last - m_first + 1 + cy - 1) / cy, n_tiles = tiles_x * tiles_y;
+      const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
+      kernel<<<grid, nw * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+      *name = nm;
+      return cudaGetLastError();
+    };
+    if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
+    if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
+    return launch(easu_h_quad2x_kernel<4, 6>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");
   }
 
   int BW = max_footprint(p.out.w, 0, kTileW, p.c0x, p.c0z, true);

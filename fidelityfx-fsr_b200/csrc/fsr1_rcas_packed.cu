@@ -15,6 +15,7 @@
 // halves (h2rcp); the resolve reciprocal is the packed APrxMedRcpH2 (ffx_a.h:1815).  Against the fp32
 // oracle on the same half input: <= 2e-3 (tolerance 1e-2).  min/max are the non-propagating half2 forms, so
 // the 0*inf NaNs of flat black / white neighbourhoods drop out exactly as with HLSL min/max (:756-759).
+#include <stdlib.h>
 #include "fsr1_common.cuh"
 
 namespace fsr1 {
@@ -60,13 +61,26 @@ __device__ __forceinline__ Row3 load_pair(const RcasParams& p, int x, int y) {
   return to_soa(v);
 }
 
+// 1/a for two non-negative halves.  kNewton: packed bit-trick seed (ffx_a.h:1815's magic) + two Newton steps on
+// the fp16 pipe (a == 0 overflows to +inf after the second step, exactly what the limiter logic needs);
+// otherwise rcp.approx.f32 on the unpacked halves (MUFU).
+template <bool kNewton> __device__ __forceinline__ __half2 rcp_pos(__half2 a) {
+  if (!kNewton) return h2rcp(a);
+  const __half2 two = __float2half2_rn(2.0f);
+  __half2 b = uh2(0x778d778du - hu2(a));
+  b = __hmul2(b, __hfma2(__hneg2(b), a, two));
+  return __hmul2(b, __hfma2(__hneg2(b), a, two));
+}
+
+// lobe of one channel for two pixels:  max(-hitMin, hitMax) = -min( min(mn4,e)/(4 mx4), (1-max(mx4,e))/(4-4 mn4) )
+template <bool kNewton>
 __device__ __forceinline__ __half2 lobe_channel(__half2 b, __half2 d, __half2 e, __half2 f, __half2 h) {
   const __half2 mn4 = __hmin2(__hmin2(b, d), __hmin2(f, h));
   const __half2 mx4 = __hmax2(__hmax2(b, d), __hmax2(f, h));
   const __half2 k4 = __float2half2_rn(4.0f), k1 = __float2half2_rn(1.0f), km4 = __float2half2_rn(-4.0f);
-  const __half2 hitMin = __hmul2(__hmin2(mn4, e), h2rcp(__hmul2(k4, mx4)));
-  const __half2 hitMax = __hmul2(__hsub2(k1, __hmax2(mx4, e)), h2rcp(__hfma2(k4, mn4, km4)));
-  return __hmax2(__hneg2(hitMin), hitMax);
+  const __half2 hitMin = __hmul2(__hmin2(mn4, e), rcp_pos<kNewton>(__hmul2(k4, mx4)));
+  const __half2 negHitMax = __hmul2(__hsub2(k1, __hmax2(mx4, e)), rcp_pos<kNewton>(__hfma2(km4, mn4, k4)));
+  return __hneg2(__hmin2(hitMin, negHitMax));  // __hmin2 drops the 0*inf NaN of a flat black / white ring
 }
 
 __device__ __forceinline__ __half2 resolve_channel(__half2 lobe, __half2 rcpL, __half2 b, __half2 d, __half2 e,
@@ -75,18 +89,21 @@ __device__ __forceinline__ __half2 resolve_channel(__half2 lobe, __half2 rcpL, _
   return __hmul2(__hfma2(lobe, ring, e), rcpL);
 }
 
-template <bool kChecked, bool kClamp>
+template <bool kChecked, bool kClamp, bool kNewton>
 __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, int lane) {
   const __half2 sharp = uh2(p.sharp_h2);
   const __half2 kLimit = __float2half2_rn(-0.1875f), kZero = __float2half2_rn(0.0f);
   const uint32_t one = 0x3c003c00u;
   const bool writer = lane >= 1 && lane <= 30 && (!kChecked || x < p.out.w);
-  Row3 prev = load_pair<kChecked, kClamp>(p, x, ys - 1), cur = load_pair<kChecked, kClamp>(p, x, ys);
+  // all kRows+2 rows are requested up front: kRows+2 independent 16-byte loads in flight per lane
+  Row3 rows[kRows + 2];
+#pragma unroll
+  for (int r = 0; r < kRows + 2; r++) rows[r] = load_pair<kChecked, kClamp>(p, x, ys - 1 + r);
 #pragma unroll
   for (int r = 0; r < kRows; r++) {
     const int y = ys + r;
     if (kChecked && y >= p.y1) break;  // warp-uniform
-    const Row3 next = load_pair<kChecked, kClamp>(p, x, y + 1);
+    const Row3 prev = rows[r], cur = rows[r + 1], next = rows[r + 2];
     // d = (left lane's pixel1, my pixel0), f = (my pixel1, right lane's pixel0)
     const __half2 dR = uh2(__byte_perm(__shfl_up_sync(0xffffffffu, hu2(cur.r), 1), hu2(cur.r), 0x5432));
     const __half2 dG = uh2(__byte_perm(__shfl_up_sync(0xffffffffu, hu2(cur.g), 1), hu2(cur.g), 0x5432));
@@ -95,9 +112,9 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
     const __half2 fG = uh2(__byte_perm(hu2(cur.g), __shfl_down_sync(0xffffffffu, hu2(cur.g), 1), 0x5432));
     const __half2 fB = uh2(__byte_perm(hu2(cur.b), __shfl_down_sync(0xffffffffu, hu2(cur.b), 1), 0x5432));
 
-    const __half2 lR = lobe_channel(prev.r, dR, cur.r, fR, next.r);
-    const __half2 lG = lobe_channel(prev.g, dG, cur.g, fG, next.g);
-    const __half2 lB = lobe_channel(prev.b, dB, cur.b, fB, next.b);
+    const __half2 lR = lobe_channel<kNewton>(prev.r, dR, cur.r, fR, next.r);
+    const __half2 lG = lobe_channel<kNewton>(prev.g, dG, cur.g, fG, next.g);
+    const __half2 lB = lobe_channel<kNewton>(prev.b, dB, cur.b, fB, next.b);
     const __half2 lobe = __hmul2(__hmax2(kLimit, __hmin2(__hmax2(lR, __hmax2(lG, lB)), kZero)), sharp);
     // APrxMedRcpH2(4*lobe+1): packed 16-bit magic subtract (no borrow: both lanes' bits <= 0x3c00) + one Newton step
     const __half2 a = __hfma2(__float2half2_rn(4.0f), lobe, __float2half2_rn(1.0f));
@@ -117,12 +134,10 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
         *reinterpret_cast<uint2*>(o) = make_uint2(rg0, b0);
       }
     }
-    prev = cur;
-    cur = next;
   }
 }
 
-template <bool kClamp>
+template <bool kClamp, bool kNewton>
 __global__ void __launch_bounds__(32 * kWarps) rcas_h_packed_kernel(const RcasParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kSpan - 2;  // even -> every lane's pair is 16-byte aligned
@@ -131,9 +146,9 @@ __global__ void __launch_bounds__(32 * kWarps) rcas_h_packed_kernel(const RcasPa
   if (ys >= p.y1) return;  // whole warp
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kRows < p.in.h && ys + kRows <= p.y1;
   if (interior)
-    rcas_rows<false, kClamp>(p, x, ys, lane);
+    rcas_rows<false, kClamp, kNewton>(p, x, ys, lane);
   else
-    rcas_rows<true, kClamp>(p, x, ys, lane);
+    rcas_rows<true, kClamp, kNewton>(p, x, ys, lane);
 }
 
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name) {
@@ -141,11 +156,17 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
   const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + kWarps * kRows - 1) / (kWarps * kRows), 1);
-  if (p.clamp)
-    rcas_h_packed_kernel<true><<<grid, 32 * kWarps, 0, s>>>(p);
-  else
-    rcas_h_packed_kernel<false><<<grid, 32 * kWarps, 0, s>>>(p);
-  *name = "rcas_h_packed<2px,4rows,shfl60>";
+  static int variant = -1;  // development knob: FSR1_RCAS_VARIANT = 0 (MUFU reciprocals), 1 (Newton on the fp16 pipe)
+  if (variant < 0) { const char* e = getenv("FSR1_RCAS_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (variant == 1) {
+    if (p.clamp) rcas_h_packed_kernel<true, true><<<grid, 32 * kWarps, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, true><<<grid, 32 * kWarps, 0, s>>>(p);
+    *name = "rcas_h_packed<2px,4rows,shfl60,newton>";
+  } else {
+    if (p.clamp) rcas_h_packed_kernel<true, false><<<grid, 32 * kWarps, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, false><<<grid, 32 * kWarps, 0, s>>>(p);
+    *name = "rcas_h_packed<2px,4rows,shfl60,mufu>";
+  }
   return cudaGetLastError();
 }
 
