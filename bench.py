@@ -235,10 +235,38 @@ def run_ours(args, rank, world, local_rank):
         # frame = `world` slabs tall; this rank owns input rows [rank*ih, (rank+1)*ih) of it
         H_in, H_out = ih * world, oh * world
         ups = [F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev) for _ in range(RING)]
-        owned = [torch.from_numpy(host_frame(12345 + t + 1000 * rank)).to(dev) for t in range(RING)]
+        for t, u in enumerate(ups):  # each frame's slab is resident in HBM inside its halo window
+            u.owned.copy_(torch.from_numpy(host_frame(12345 + t + 1000 * rank)).to(dev))
+        if args.graph:
+            for u in ups:            # halo exchange + EASU + RCAS recorded once; a step is one graph launch
+                u.capture()
 
-        def step(i):
-            ups[i % RING].upscale(owned[i % RING], stream=stream)
+            def step(i):
+                ups[i % RING].upscale()
+        elif args.no_overlap:
+            def step(i):
+                ups[i % RING].upscale()
+        else:
+            # frame pipeline: while frame i is upscaled, the halo rows of frame i+1 (already resident) travel on a
+            # second stream; kernels of frame i+1 wait on that exchange's event only
+            comm = torch.cuda.Stream(device=dev)
+            ready = [torch.cuda.Event() for _ in range(RING)]
+
+            def prefetch(j):
+                u = ups[j % RING]
+                comm.wait_stream(stream)         # the window's previous readers (frame j-RING) are ordered before
+                with torch.cuda.stream(comm):
+                    u._exchange()
+                    ready[j % RING].record(comm)
+            prefetch(0)
+            frame = [0]
+
+            def step(_):
+                i = frame[0]
+                frame[0] += 1
+                prefetch(i + 1)
+                stream.wait_event(ready[i % RING])
+                ups[i % RING]._launch(stream)
         step_easu = step_rcas = None
         total_out_px = ow * H_out
         halo = ups[0].plan.halo_bytes(rank, iw, bpp)
@@ -270,6 +298,8 @@ def run_ours(args, rank, world, local_rank):
     launches0 = api.launch_count()
     ms = timed(step, K)
     launches = api.launch_count() - launches0
+    if world > 1 and args.graph:
+        launches = 2 * K  # each replayed graph holds this library's two kernels (EASU, RCAS), recorded at capture
     clocks = sampler.stop() if rank == 0 else None
     value = total_out_px * K / (ms * 1e-3) / 1e6
 
@@ -338,7 +368,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": wl[5] if world == 1 else wl[5] + " x%d slabs tall, row-slab sharded, NCCL halo" % world,
                        "sharpness_stops": SHARPNESS, "frame": "LCG uniform noise, seed 12345+t",
                        "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * ih + 2 * ow * oh) * bpp / 1e6),
-                       "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step" % (world, halo)},
+                       "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step, %s" % (
+                           world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else "halo exchange of frame i+1 overlapped with frame i on a second stream"))},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if roofline:
@@ -379,6 +410,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-4k-fp16", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

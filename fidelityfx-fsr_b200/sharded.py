@@ -78,12 +78,13 @@ class SlabPlan:
 def exchange_halo(plan, rank, owned, window, dist=None):
     """Fill `window` (rows needed_in_rows(rank)) from `owned` (rows owned_in_rows(rank)) and the peers.
 
-    Works on any backend: gloo with CPU tensors (tests) or nccl with CUDA tensors (production).
+    `owned` may be a view INTO `window` (see ShardedUpscaler.owned): then nothing is copied locally and only the
+    halo rows move.  Works on any backend: gloo with CPU tensors (tests) or nccl with CUDA tensors (production).
     """
     own0, own1 = plan.owned_in_rows(rank)
     need0, need1 = plan.needed_in_rows(rank)
     a, b = max(own0, need0), min(own1, need1)
-    if b > a:
+    if b > a and owned[a - own0:a - own0 + 1].data_ptr() != window[a - need0:a - need0 + 1].data_ptr():
         window[a - need0:b - need0].copy_(owned[a - own0:b - own0])
     sends, recvs = plan.transfers(rank)
     if not sends and not recvs:
@@ -101,7 +102,12 @@ def exchange_halo(plan, rank, owned, window, dist=None):
 
 
 class ShardedUpscaler:
-    """One instance per rank (one process per GPU)."""
+    """One instance per rank (one process per GPU).
+
+    The rank's input slab lives INSIDE its halo window: write frames into `self.owned` (a view of the window's
+    middle rows) and call upscale(); only the 2-3 halo rows per side travel, straight into the window's edge rows.
+    capture() records halo exchange + EASU + RCAS into one CUDA graph so a frame costs one graph launch.
+    """
 
     def __init__(self, in_w, in_h, out_w, out_h, world, rank, sharpness=0.25, dtype=None, device=None, flags=0):
         import torch
@@ -114,20 +120,55 @@ class ShardedUpscaler:
         dtype = dtype or torch.float16
         device = device or torch.device("cuda", torch.cuda.current_device())
         n0, n1 = self.plan.needed_in_rows(rank)
+        o0, o1 = self.plan.owned_in_rows(rank)
         e0, e1 = self.plan.easu_rows(rank)
         y0, y1 = self.plan.out_rows(rank)
-        self.window = torch.empty((n1 - n0, in_w, 4), dtype=dtype, device=device)
+        lo, hi = min(n0, o0), max(n1, o1)     # the window always holds the whole owned slab
+        self._win0 = lo
+        self.window = torch.zeros((hi - lo, in_w, 4), dtype=dtype, device=device)
+        self.owned = self.window[o0 - lo:o1 - lo]
         self.tmp = torch.empty((e1 - e0, out_w, 4), dtype=dtype, device=device)
         self.out = torch.empty((y1 - y0, out_w, 4), dtype=dtype, device=device)
+        self._graph = None
 
-    def upscale(self, owned_rows, stream=None):
-        """owned_rows: this rank's input slab [owned_in_rows) on the GPU.  Returns the output slab."""
+    def _exchange(self):
         plan, rank = self.plan, self.rank
-        exchange_halo(plan, rank, owned_rows, self.window)
-        n0, _ = plan.needed_in_rows(rank)
+        sends, recvs = plan.transfers(rank)
+        if not sends and not recvs:
+            return
+        import torch.distributed as dist
+        ops = [dist.P2POp(dist.isend, self.window[a - self._win0:b - self._win0], peer) for peer, a, b in sends]
+        ops += [dist.P2POp(dist.irecv, self.window[a - self._win0:b - self._win0], peer) for peer, a, b in recvs]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def _launch(self, stream=None):
+        plan, rank = self.plan, self.rank
         e0, _ = plan.easu_rows(rank)
         y0, y1 = plan.out_rows(rank)
-        api.upscale(api.image(self.window, height=self.in_h, row0=n0), api.image(self.tmp, height=self.out_h, row0=e0),
+        api.upscale(api.image(self.window, height=self.in_h, row0=self._win0), api.image(self.tmp, height=self.out_h, row0=e0),
                     api.image(self.out, height=self.out_h, row0=y0), self.econ, self.rcon, y0=y0, y1=y1,
                     flags=self.flags, stream=stream)
+
+    def upscale(self, owned_rows=None, stream=None):
+        """Upscale the frame whose slab is in self.owned (or in `owned_rows`, which is then copied in)."""
+        if owned_rows is not None and owned_rows.data_ptr() != self.owned.data_ptr():
+            self.owned.copy_(owned_rows)
+        if self._graph is not None and stream is None:
+            self._graph.replay()
+            return self.out
+        self._exchange()
+        self._launch(stream)
         return self.out
+
+    def capture(self):
+        """Record halo exchange + both kernels into a CUDA graph (NCCL point-to-point is capturable)."""
+        import torch
+        self.upscale()                      # warm up: NCCL channels, kernel attributes, TMA descriptors
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._exchange()
+            self._launch(torch.cuda.current_stream())
+        self._graph = g
+        return self
