@@ -142,49 +142,69 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
 // =======================================================================================================
 constexpr int kTileW = 64, kTileH = 16;
 
+// dynamic shared memory: [tile0][tile1][luma][terms][2 mbarriers], every part 128-byte aligned
+__host__ __device__ inline size_t pairs_tile_stride(int BW, int BH) { return ((size_t)BW * BH * 8 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
-  size_t n = (size_t)BW * BH, off = (n * 8 + 15) & ~(size_t)15;
-  off = (off + n * 4 + 15) & ~(size_t)15;
-  off = (off + (size_t)(BW - 2) * (BH - 2) * 16 + 15) & ~(size_t)15;
-  return off + 16 + 128;  // + barrier + slack for the manual 128B alignment
+  size_t off = 2 * pairs_tile_stride(BW, BH);
+  off += ((size_t)BW * BH * 4 + 127) & ~(size_t)127;
+  off += ((size_t)(BW - 2) * (BH - 2) * 16 + 127) & ~(size_t)127;
+  return off + 16 + 128;  // + barriers + slack for the manual 128B alignment
 }
 
 __global__ void __launch_bounds__(kThreads, 3)
-easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH) {
+easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH,
+                    const int tiles_x, const int n_tiles) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte align by OFFSET (pointer arithmetic on the shared array keeps the address space -> LDS/STS)
   unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int n = BW * BH;
-  uint2* tile = reinterpret_cast<uint2*>(base);
-  size_t off = ((size_t)n * 8 + 15) & ~(size_t)15;
-  float* L = reinterpret_cast<float*>(base + off);
-  off = (off + (size_t)n * 4 + 15) & ~(size_t)15;
-  float4* S = reinterpret_cast<float4*>(base + off);
-  off = (off + (size_t)(BW - 2) * (BH - 2) * 16 + 15) & ~(size_t)15;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + off);
-
+  const size_t tstride = pairs_tile_stride(BW, BH);
+  float* L = reinterpret_cast<float*>(base + 2 * tstride);
+  float4* S = reinterpret_cast<float4*>(base + 2 * tstride + (((size_t)n * 4 + 127) & ~(size_t)127));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(S) +
+                                              (((size_t)(BW - 2) * (BH - 2) * 16 + 127) & ~(size_t)127));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ox0 = blockIdx.x * kTileW, oy0 = p.y0 + blockIdx.y * kTileH;
-  int fx0, fy0;
-  float dummy;
-  easu_pos(ox0, p.c0x, p.c0z, fx0, dummy);
-  easu_pos(oy0, p.c0y, p.c0w, fy0, dummy);
-  fx0 = (fx0 - 1) & ~1;  // box origin = first tap column/row of the tile's first pixel; the column is rounded
-  fy0 -= 1;              // down to even: TMA traps unless the box starts on a 16-byte boundary (2 texels)
-
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, (uint32_t)n * 8u);
-    tma_load_2d(tile, &tmap, fx0, fy0 - p.in.row0, bar);
+  // box origin of tile t = first tap column/row of its first pixel; the column is rounded down to even because
+  // TMA traps unless the box starts on a 16-byte boundary (2 texels)
+  auto origin = [&](int t, int& ox0, int& oy0, int& fx0, int& fy0) {
+    ox0 = (t % tiles_x) * kTileW;
+    oy0 = p.y0 + (t / tiles_x) * kTileH;
+    float dummy;
+    easu_pos(ox0, p.c0x, p.c0z, fx0, dummy);
+    easu_pos(oy0, p.c0y, p.c0w, fy0, dummy);
+    fx0 = (fx0 - 1) & ~1;
+    fy0 -= 1;
+  };
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tiles) {
+    int a, b, fx, fy;
+    origin(t, a, b, fx, fy);
+    mbar_expect_tx(&bar[0], (uint32_t)n * 8u);
+    tma_load_2d(base, &tmap, fx, fy - p.in.row0, &bar[0]);
   }
-  mbar_wait(bar, 0);
+  for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
+  const int bsel = it & 1;
+  if (tid == 0 && t + (int)gridDim.x < n_tiles) {  // prefetch the next tile into the other buffer
+    int a, b, fx, fy;
+    origin(t + gridDim.x, a, b, fx, fy);
+    fence_proxy_async();
+    mbar_expect_tx(&bar[bsel ^ 1], (uint32_t)n * 8u);
+    tma_load_2d(base + (bsel ^ 1) * tstride, &tmap, fx, fy - p.in.row0, &bar[bsel ^ 1]);
+  }
+  uint2* tile = reinterpret_cast<uint2*>(base + bsel * tstride);
+  int ox0, oy0, fx0, fy0;
+  origin(t, ox0, oy0, fx0, fy0);
+  mbar_wait(&bar[bsel], (it >> 1) & 1);
 
   if (fx0 < 0 || fy0 < 0 || fx0 + BW > p.in.w || fy0 + BH > p.in.h) {  // border tiles only (CTA-uniform)
     clamp_fixup(tile, BW, BH, fx0, fy0, p.in.w, p.in.h, lane, warp);
+    fence_proxy_async();
     __syncthreads();
   }
 
@@ -298,6 +318,8 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
       *reinterpret_cast<uint2*>(orow + (size_t)ox * 8) = make_uint2(h22u(oRG_A), h22u(oBA_A));
     }
   }
+  __syncthreads();  // L, S and this tile buffer are free again
+  }  // persistent tile loop
 }
 
 // =======================================================================================================
@@ -565,9 +587,12 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const dim3 grid((p.out.w + kTileW - 1) / kTileW, (p.y1 - p.y0 + kTileH - 1) / kTileH, 1);
-  easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH);
-  *name = "easu_h_pairs<64x16,tma>";
+  const int tiles_x = (p.out.w + kTileW - 1) / kTileW, n_tiles = tiles_x * ((p.y1 - p.y0 + kTileH - 1) / kTileH);
+  int per_sm = 3;
+  while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 220 * 1024) per_sm--;
+  const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
+  easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
+  *name = "easu_h_pairs<64x16,persistent,tma2>";
   return cudaGetLastError();
 }
 

@@ -3,7 +3,7 @@
 Reference: sample/src/DX12/FSR_Filter.h:27-45 and FSR_Filter.cpp:41-141 (VK twin sample/src/VK/FSR_Filter.cpp).
 Same method names, argument meaning and call pattern; D3D12 objects are replaced by torch CUDA tensors
 (device memory) and a CUDA stream (the command list).  The C++ twin for native callers is
-csrc/../fsr_filter.hpp.
+fsr_filter.hpp (same directory).
 """
 from dataclasses import dataclass
 

@@ -54,3 +54,18 @@ def test_error_strings_and_validation_without_gpu():
     assert L.fsr1_easu_input_rows(econ, 64, 20, 40, ctypes.byref(a), ctypes.byref(b)) == 0
     assert (a.value, b.value) == (8, 21)  # rows floor((20+.5)/2-.5)-1 .. floor((39+.5)/2-.5)+2
     assert L.fsr1_launch_count() == 0
+
+
+def test_cpp_filter_mirror_compiles_and_links(tmp_path):
+    """fidelityfx-fsr_b200/fsr_filter.hpp: the C++ twin of the reference's FSR_Filter over the C ABI."""
+    import subprocess
+    src = tmp_path / "f.cpp"
+    src.write_text('#include "fidelityfx-fsr_b200/fsr_filter.hpp"\n'
+                   'int main(){ fsr1::FSR_Filter f; f.OnCreate(); fsr1::State s; s.renderWidth = 8;\n'
+                   '  AU1 c[16]; FsrEasuCon(c, c+4, c+8, c+12, 8.f, 8.f, 8.f, 8.f, 16.f, 16.f);\n'
+                   '  return (fsr1_abi_version() == 1 && c[0] == 0x3f000000u) ? 0 : 1; }\n')
+    exe = tmp_path / "f"
+    libdir = os.path.join(ROOT, "fidelityfx-fsr_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", ROOT, str(src), "-o", str(exe), "-L", libdir, "-lfsr1_b200",
+                           "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
