@@ -130,15 +130,41 @@ class ShardedUpscaler:
         self.tmp = torch.empty((e1 - e0, out_w, 4), dtype=dtype, device=device)
         self.out = torch.empty((y1 - y0, out_w, 4), dtype=dtype, device=device)
         self._graph = None
+        import os
+        self.halo_mode = os.environ.get("FSR1_HALO_MODE", "a2a")   # "p2p": batch_isend_irecv; "a2a": one all_to_all
+
+    def _build_exchange(self):
+        """Halo transfers as views of the window, built once: rows to send / receive per peer."""
+        import torch
+        plan, rank, w0 = self.plan, self.rank, self._win0
+        sends, recvs = plan.transfers(rank)
+        self._sends = [(peer, self.window[a - w0:b - w0]) for peer, a, b in sends]
+        self._recvs = [(peer, self.window[a - w0:b - w0]) for peer, a, b in recvs]
+        empty = self.window[0:0]
+        # the same transfers phrased as ONE all-to-all whose only non-empty entries are the neighbours: a single
+        # NCCL group / work object per frame instead of one per send and receive (host launch cost, not bytes)
+        self._a2a_in = [empty] * self.world
+        self._a2a_out = [empty] * self.world
+        multi = False
+        for peer, t in self._sends:
+            multi |= self._a2a_in[peer].numel() > 0
+            self._a2a_in[peer] = t
+        for peer, t in self._recvs:
+            multi |= self._a2a_out[peer].numel() > 0
+            self._a2a_out[peer] = t
+        self._a2a_ok = not multi
 
     def _exchange(self):
-        plan, rank = self.plan, self.rank
-        sends, recvs = plan.transfers(rank)
-        if not sends and not recvs:
+        if not hasattr(self, "_sends"):
+            self._build_exchange()
+        if not self._sends and not self._recvs:
             return
         import torch.distributed as dist
-        ops = [dist.P2POp(dist.isend, self.window[a - self._win0:b - self._win0], peer) for peer, a, b in sends]
-        ops += [dist.P2POp(dist.irecv, self.window[a - self._win0:b - self._win0], peer) for peer, a, b in recvs]
+        if self.halo_mode == "a2a" and self._a2a_ok:
+            dist.all_to_all(self._a2a_out, self._a2a_in)
+            return
+        ops = [dist.P2POp(dist.isend, t, peer) for peer, t in self._sends]
+        ops += [dist.P2POp(dist.irecv, t, peer) for peer, t in self._recvs]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
