@@ -124,7 +124,12 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
   const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
   cudaError_t e = cudaErrorNotSupported;
   const char* name = "";
-  if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) e = launch_easu_h_tiled(p, s, &name);
+  if (flags & FSR1_FLAG_H_REFERENCE) {
+    if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
+    e = launch_easu_href(p, s, &name);
+  } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    e = launch_easu_h_tiled(p, s, &name);
+  }
   if (e == cudaErrorNotSupported) e = launch_easu_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;
@@ -156,7 +161,12 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
   cudaError_t e = cudaErrorNotSupported;
   const char* name = "";
-  if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) e = launch_rcas_h_packed(p, s, &name);
+  if (flags & FSR1_FLAG_H_REFERENCE) {
+    if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
+    e = launch_rcas_href(p, s, &name);
+  } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    e = launch_rcas_h_packed(p, s, &name);
+  }
   if (e == cudaErrorNotSupported) e = launch_rcas_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;

@@ -59,7 +59,11 @@ enum {
   FSR1_FLAG_EXACT = 1u << 1,        /* fp32 images only: no FMA contraction, IEEE division — bit-identical
                                        to the reference source compiled with -ffp-contract=off          */
   FSR1_FLAG_FORCE_DIRECT = 1u << 2, /* skip the TMA/shared-memory kernels, use the direct-load kernels   */
-  FSR1_FLAG_NO_RCAS = 1u << 3       /* fsr1_upscale*: EASU straight to the output (bUseRcas == false)   */
+  FSR1_FLAG_NO_RCAS = 1u << 3,      /* fsr1_upscale*: EASU straight to the output (bUseRcas == false)   */
+  FSR1_FLAG_H_REFERENCE = 1u << 4   /* fp16 images only: the literal FsrEasuH / FsrRcasH arithmetic (packed-half
+                                       algorithm, half magic numbers, per-operation half rounding), bit-identical
+                                       to the reference's H source; a parity path, slower and LESS accurate than
+                                       the default fp16 kernels (see DESIGN.md "numerics")                  */
 };
 
 /* A (window of a) device image.  `width`/`height` are the logical size of the whole image; `data`

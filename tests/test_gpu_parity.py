@@ -121,6 +121,34 @@ def test_against_committed_golden_vectors(kind, tag):
     assert np.array_equal(r.view(np.uint32), G[key].view(np.uint32))
 
 
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_h_reference_mode_is_bit_identical_to_the_packed_half_source(shape, gen):
+    """FSR1_FLAG_H_REFERENCE = the literal FsrEasuH / FsrRcasH arithmetic.  The H-path oracle is bit-equal to the
+    reference's own H source compiled for the host (tests/test_oracle.py), so this pins the kernels to it."""
+    iw, ih, ow, oh = shape
+    src = F.to_half(getattr(F, gen)(iw, ih, 34))
+    want = ol.easu(src, ow, oh)                      # half input -> the H-path model
+    got = gpu_easu(src, ow, oh, api.FLAG_H_REFERENCE)
+    assert api.last_kernel().startswith("easu_href")
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+    for clamp in (0, api.FLAG_RCAS_CLAMP):
+        for sharp in (0.0, 0.25, 1.0):
+            r = gpu_rcas(want, sharp, api.FLAG_H_REFERENCE | clamp)
+            assert np.array_equal(r.view(np.uint16), ol.rcas(want, ol.rcas_con(sharp), bool(clamp)).view(np.uint16))
+
+
+def test_h_reference_mode_against_golden_vectors():
+    for kind in ("uniform", "structured"):
+        for tag, (ow, oh) in GSIZES.items():
+            src_h = G[kind + "_in_f16"].view(np.float16)
+            got = gpu_easu(src_h, ow, oh, api.FLAG_H_REFERENCE)
+            assert np.array_equal(got.view(np.uint16), G["%s_%s_easu_h16" % (kind, tag)])
+            key = "%s_%s_rcas_s0.25_c0_h16" % (kind, tag)
+            r = gpu_rcas(G["%s_%s_easu_h16" % (kind, tag)].view(np.float16), 0.25, api.FLAG_H_REFERENCE)
+            assert np.array_equal(r.view(np.uint16), G[key])
+
+
 def e2e_check(got, want, what):
     """End to end (EASU -> fp16 intermediate -> RCAS) against the fp32 oracle end to end.  RCAS amplifies any
     difference in its input by up to 1/(1+4*lobe) + ... ~ 4-7x, so the per-kernel bound (1e-2 each, asserted in the
