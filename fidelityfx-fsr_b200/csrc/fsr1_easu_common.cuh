@@ -1,0 +1,119 @@
+// fsr1_easu_common.cuh — pieces shared by the tiled EASU kernels (fp16 and fp32 storage): PTX wrappers for
+// mbarrier + TMA, the per-texel and per-pixel fp32 analysis, and the host-side tensor-map helpers.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+#include "fsr1_common.cuh"
+
+namespace fsr1 {
+
+// ---- PTX wrappers: mbarrier + TMA ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- small helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 h2c(float v) { return __float2half2_rn(v); }
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
+// FsrEasuSetF without the bilinear weight: (dirX, dirY, lenX^2 + lenY^2) of the texel whose luma is lC.
+__device__ __forceinline__ float4 texel_terms(float lA, float lB, float lC, float lD, float lE) {
+  const float dirX = lD - lB, dirY = lE - lA;
+  const float lenX = sat(fabsf(dirX) * prx_lo_rcp(fmaxf(fabsf(lD - lC), fabsf(lC - lB))));
+  const float lenY = sat(fabsf(dirY) * prx_lo_rcp(fmaxf(fabsf(lE - lC), fabsf(lC - lA))));
+  return make_float4(dirX, dirY, fmaf(lenX, lenX, lenY * lenY), 0.0f);
+}
+
+// Per-pixel filter shape from the blended (dir, len): the coefficients the tap loop needs.  fp32.
+struct Shape { float qa, qb, qc, lob, clp; };
+__device__ __forceinline__ Shape pixel_shape(float dx, float dy, float len) {
+  const float dirR = fmaf(dx, dx, dy * dy);
+  const bool zro = dirR < (1.0f / 32768.0f);
+  const float rs = zro ? 1.0f : prx_lo_rsq(dirR);
+  dx = (zro ? 1.0f : dx) * rs;
+  dy *= rs;
+  len *= 0.5f;
+  len *= len;
+  const float dx2 = dx * dx, dy2 = dy * dy;
+  const float stretch = (dx2 + dy2) * prx_lo_rcp(fmaxf(fabsf(dx), fabsf(dy)));
+  const float l2x = fmaf(stretch - 1.0f, len, 1.0f), l2y = fmaf(-0.5f, len, 1.0f);
+  Shape s;
+  s.lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
+  s.clp = prx_lo_rcp(s.lob);
+  const float X2 = l2x * l2x, Y2 = l2y * l2y;
+  s.qa = fmaf(X2, dx2, Y2 * dy2);
+  s.qc = fmaf(X2, dy2, Y2 * dx2);
+  s.qb = (dx * dy * 2.0f) * (X2 - Y2);
+  return s;
+}
+
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// Same float arithmetic as easu_pos on the device.
+static inline int host_fp(int o, float scale, float offset) {
+  volatile float m = (float)o * scale;
+  volatile float s = m + offset;
+  return (int)floorf(s);
+}
+
+static inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace fsr1

@@ -1,0 +1,222 @@
+// fsr1_easu_f32.cu — tiled EASU for RGBA32F images at exactly 2x (the SAMPLE_SLOW_FALLBACK precision of
+// BASELINE configs[3]).  Same structure as easu_h_quad2x_kernel (fsr1_easu_tiled.cu): persistent CTAs, TMA
+// box load double-buffered on two mbarriers (here a 3-D tensor {4 floats, W, rows}), per-input-texel luma and
+// FsrEasuSetF terms hoisted to shared memory, a lane owns the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2)
+// that shares one 4x4 tap window.  All arithmetic is fp32 (F path, ffx-fsr/ffx_fsr1.h:239-437); the tap weights of
+// the two pixels of a row pair are computed with Blackwell's packed FFMA2/FMUL2/FADD2 (fma.rn.f32x2: two fp32
+// lanes per instruction, half the issue slots of scalar FFMA at the same pipe cost), the colour accumulation
+// with scalar FFMA.  The tap distance keeps the reference's own rotate-then-scale formulation (the expanded
+// quadratic form used by the half kernels costs ~1e-6 in fp32, too close to the 1e-5 tolerance).  Tolerance
+// against the oracle: 1e-5 (FMA contraction reorders roundings; FSR1_FLAG_EXACT = the bit-exact direct kernel).
+#include "fsr1_easu_common.cuh"
+
+namespace fsr1 {
+
+constexpr int kFQCX = 32, kFQBW = kFQCX + 4, kFQSW = kFQBW - 2;
+template <int NW> struct FQuadCfg {
+  static constexpr int kCY = 2 * NW, kBH = kCY + 3, kSH = kBH - 2, kElems = kFQBW * kBH;
+  static constexpr int kPad = ((kElems * 16 + 127) / 128) * 128 / 16;
+};
+template <int NW> struct __align__(128) FQuadSmem {
+  float4 tile[2][FQuadCfg<NW>::kPad];
+  float4 S[kFQSW * FQuadCfg<NW>::kSH];
+  float L[FQuadCfg<NW>::kElems];
+  uint64_t bar[2];
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// Per-pixel filter shape in the reference's own formulation (rotation * anisotropic scale), fp32:
+//   v = (ox*cxx + oy*cxy, ox*cyx + oy*cyy),  cxx = dx*l2x, cxy = dy*l2x, cyx = -dy*l2y, cyy = dx*l2y
+struct ShapeR { float cxx, cxy, cyx, cyy, lob, clp; };
+__device__ __forceinline__ ShapeR pixel_shape_rot(float dx, float dy, float len) {
+  const float dirR = fmaf(dx, dx, dy * dy);
+  const bool zro = dirR < (1.0f / 32768.0f);
+  const float rs = zro ? 1.0f : prx_lo_rsq(dirR);
+  dx = (zro ? 1.0f : dx) * rs;
+  dy *= rs;
+  len *= 0.5f;
+  len *= len;
+  const float stretch = fmaf(dx, dx, dy * dy) * prx_lo_rcp(fmaxf(fabsf(dx), fabsf(dy)));
+  const float l2x = fmaf(stretch - 1.0f, len, 1.0f), l2y = fmaf(-0.5f, len, 1.0f);
+  ShapeR s;
+  s.lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
+  s.clp = prx_lo_rcp(s.lob);
+  s.cxx = dx * l2x; s.cxy = dy * l2x; s.cyx = -dy * l2y; s.cyy = dx * l2y;
+  return s;
+}
+
+// One row pair (A: px=.25, B: px=.75) of the quad; kBottom selects py=.75.
+template <bool kBottom>
+__device__ __forceinline__ void fquad_pair(const float4 (&t)[4][4], const ShapeR& sA, const ShapeR& sB, float3 mn, float3 mx,
+                                           float4& outA, float4& outB) {
+  const float2 cxx = f2(sA.cxx, sB.cxx), cxy = f2(sA.cxy, sB.cxy), cyx = f2(sA.cyx, sB.cyx), cyy = f2(sA.cyy, sB.cyy);
+  const float2 lob = f2(sA.lob, sB.lob);
+  float3 aA = make_float3(0.f, 0.f, 0.f), aB = make_float3(0.f, 0.f, 0.f);
+  float2 aW = f2(0.f, 0.f);
+  constexpr float py = kBottom ? 0.75f : 0.25f;
+#define FSR1_FQTAP(R, K)                                                                                      \
+  {                                                                                                           \
+    constexpr float oxA = (float)((K)-1) - 0.25f, oxB = (float)((K)-1) - 0.75f, oy = (float)((R)-1) - py;       \
+    const float2 vx = __ffma2_rn(f2(oxA, oxB), cxx, __fmul2_rn(f2(oy, oy), cxy));                              \
+    const float2 vy = __ffma2_rn(f2(oxA, oxB), cyx, __fmul2_rn(f2(oy, oy), cyy));                              \
+    float2 d2 = __ffma2_rn(vx, vx, __fmul2_rn(vy, vy));                                                       \
+    d2.x = fminf(d2.x, sA.clp);                                                                               \
+    d2.y = fminf(d2.y, sB.clp);                                                                               \
+    float2 wb = __ffma2_rn(f2(0.4f, 0.4f), d2, f2(-1.f, -1.f));                                                \
+    float2 wa = __ffma2_rn(lob, d2, f2(-1.f, -1.f));                                                          \
+    wb = __fmul2_rn(wb, wb);                                                                                  \
+    wa = __fmul2_rn(wa, wa);                                                                                  \
+    wb = __ffma2_rn(f2(1.5625f, 1.5625f), wb, f2(-0.5625f, -0.5625f));                                        \
+    const float2 w = __fmul2_rn(wb, wa);                                                                      \
+    const float4 c = t[R][K];                                                                                 \
+    aA.x = fmaf(c.x, w.x, aA.x); aA.y = fmaf(c.y, w.x, aA.y); aA.z = fmaf(c.z, w.x, aA.z);                    \
+    aB.x = fmaf(c.x, w.y, aB.x); aB.y = fmaf(c.y, w.y, aB.y); aB.z = fmaf(c.z, w.y, aB.z);                    \
+    aW = __fadd2_rn(aW, w);                                                                                   \
+  }
+  FSR1_FQTAP(0, 1) FSR1_FQTAP(0, 2) FSR1_FQTAP(2, 0) FSR1_FQTAP(2, 1)   // the reference's order: b c i j f e k l h g o n
+  FSR1_FQTAP(1, 1) FSR1_FQTAP(1, 0) FSR1_FQTAP(2, 2) FSR1_FQTAP(2, 3)
+  FSR1_FQTAP(1, 3) FSR1_FQTAP(1, 2) FSR1_FQTAP(3, 2) FSR1_FQTAP(3, 1)
+#undef FSR1_FQTAP
+  const float rA = __frcp_rn(aW.x), rB = __frcp_rn(aW.y);
+  outA = make_float4(fminf(mx.x, fmaxf(mn.x, aA.x * rA)), fminf(mx.y, fmaxf(mn.y, aA.y * rA)), fminf(mx.z, fmaxf(mn.z, aA.z * rA)), 1.0f);
+  outB = make_float4(fminf(mx.x, fmaxf(mn.x, aB.x * rB)), fminf(mx.y, fmaxf(mn.y, aB.y * rB)), fminf(mx.z, fmaxf(mn.z, aB.z * rB)), 1.0f);
+}
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
+                       const int n_tiles, const int mbase) {
+  using C = FQuadCfg<NW>;
+  constexpr int NT = NW * 32;
+  __shared__ FQuadSmem<NW> sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto box_x = [&](int t) { return (t % tiles_x) * kFQCX - 2; };
+  auto box_y = [&](int t) { return mbase + (t / tiles_x) * C::kCY - 1; };
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tiles) {
+    mbar_expect_tx(&sm.bar[0], C::kElems * 16u);
+    tma_load_3d(sm.tile[0], &tmap, 0, box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
+  }
+  for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
+    const int b = it & 1;
+    const int tn = t + gridDim.x;
+    if (tid == 0 && tn < n_tiles) {
+      fence_proxy_async();
+      mbar_expect_tx(&sm.bar[b ^ 1], C::kElems * 16u);
+      tma_load_3d(sm.tile[b ^ 1], &tmap, 0, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
+    }
+    float4* tile = sm.tile[b];
+    const int gx0 = box_x(t), gy0 = box_y(t);
+    mbar_wait(&sm.bar[b], (it >> 1) & 1);
+    if (gx0 < 0 || gy0 < 0 || gx0 + kFQBW > p.in.w || gy0 + C::kBH > p.in.h) {  // clamp-to-edge fix-up
+      for (int j = warp; j < C::kBH; j += NW) {
+        const int cy = clampi(gy0 + j, 0, p.in.h - 1) - gy0;
+        for (int i = lane; i < kFQBW; i += 32) {
+          const int cx = clampi(gx0 + i, 0, p.in.w - 1) - gx0;
+          if ((cx != i || cy != j) && cx >= 0 && cx < kFQBW && cy >= 0 && cy < C::kBH) tile[j * kFQBW + i] = tile[cy * kFQBW + cx];
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();
+    }
+    for (int i = tid; i < C::kElems; i += NT) {
+      const float4 c = tile[i];
+      sm.L[i] = fmaf(c.z, 0.5f, fmaf(c.x, 0.5f, c.y));
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kFQSW * C::kSH; idx += NT) {
+      const int j = idx / kFQSW, i = idx - j * kFQSW;
+      const float* c = sm.L + (j + 1) * kFQBW + (i + 1);
+      sm.S[idx] = texel_terms(c[-kFQBW], c[-1], c[0], c[1], c[kFQBW]);
+    }
+    __syncthreads();
+
+    const int oxA = (gx0 + 1 + lane) * 2 + 1;
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+      const int r = warp + q * NW;
+      const int oyT = (gy0 + 1 + r) * 2 + 1;
+      const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
+      if (oxA >= p.out.w || !(rowT || rowB)) continue;
+      float4 tp[4][4];
+      const float4* t0 = tile + r * kFQBW + lane;
+#pragma unroll
+      for (int R = 0; R < 4; R++)
+#pragma unroll
+        for (int K = 0; K < 4; K++)
+          if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kFQBW + K];
+      const float4* s0 = sm.S + r * kFQSW + lane;
+      const float4 f = s0[0], g = s0[1], j = s0[kFQSW], k = s0[kFQSW + 1];
+      const float3 mn = make_float3(fminf(fminf(tp[1][1].x, tp[1][2].x), fminf(tp[2][1].x, tp[2][2].x)),
+                                    fminf(fminf(tp[1][1].y, tp[1][2].y), fminf(tp[2][1].y, tp[2][2].y)),
+                                    fminf(fminf(tp[1][1].z, tp[1][2].z), fminf(tp[2][1].z, tp[2][2].z)));
+      const float3 mx = make_float3(fmaxf(fmaxf(tp[1][1].x, tp[1][2].x), fmaxf(tp[2][1].x, tp[2][2].x)),
+                                    fmaxf(fmaxf(tp[1][1].y, tp[1][2].y), fmaxf(tp[2][1].y, tp[2][2].y)),
+                                    fmaxf(fmaxf(tp[1][1].z, tp[1][2].z), fmaxf(tp[2][1].z, tp[2][2].z)));
+      // bilinear blends in the reference's f,g,j,k order with the constant weights of pp = .25 / .75
+      auto blend = [&](float wf, float wg, float wj, float wk) {
+        return pixel_shape_rot(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))), fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
+                           fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
+      };
+      unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 16;
+      const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
+      float4 oA, oB;
+      if (rowT) {
+        fquad_pair<false>(tp, blend(0.5625f, 0.1875f, 0.1875f, 0.0625f), blend(0.1875f, 0.5625f, 0.0625f, 0.1875f), mn, mx, oA, oB);
+        if (okA) *reinterpret_cast<float4*>(orow) = oA;
+        if (okB) *reinterpret_cast<float4*>(orow + 16) = oB;
+      }
+      if (rowB) {
+        fquad_pair<true>(tp, blend(0.1875f, 0.0625f, 0.5625f, 0.1875f), blend(0.0625f, 0.1875f, 0.1875f, 0.5625f), mn, mx, oA, oB);
+        if (okA) *reinterpret_cast<float4*>(orow + p.out.pitch) = oA;
+        if (okB) *reinterpret_cast<float4*>(orow + p.out.pitch + 16) = oB;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name) {
+  if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
+      (p.out.pitch & 15))
+    return cudaErrorNotSupported;
+  if (!(p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f)) return cudaErrorNotSupported;  // 2x only
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return cudaErrorNotSupported;
+  constexpr int NW = 4;
+  using C = FQuadCfg<NW>;
+  CUtensorMap tmap;
+  const cuuint64_t dims[3] = {4, (cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
+  const cuuint64_t strides[2] = {16, (cuuint64_t)p.in.pitch};
+  const cuuint32_t box[3] = {4, (cuuint32_t)kFQBW, (cuuint32_t)C::kBH};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorNotSupported;
+  const int k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
+  const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
+  const int tiles_x = (k_last + 1 + 1 + kFQCX - 1) / kFQCX, tiles_y = (m_last - m_first + 1 + C::kCY - 1) / C::kCY;
+  const int n_tiles = tiles_x * tiles_y;
+  const int per_sm = 4;
+  const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
+  easu_f32_quad2x_kernel<NW, per_sm><<<grid, NW * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+  *name = "easu_f32_quad2x<4w,4/sm,tma2,ffma2>";
+  return cudaGetLastError();
+}
+
+}  // namespace fsr1

@@ -30,54 +30,11 @@
 //                         (2k+1,2k+2)x(2m+1,2m+2) share one 4x4 window; a lane owns that quad, loads the 12
 //                         taps and the 4 term vectors once, and every tap offset is a compile-time constant.
 //                         Persistent CTAs, TMA double-buffered: tile i+1 loads while tile i computes.
-#include <cuda.h>
-#include <stdlib.h>
-#include "fsr1_common.cuh"
+#include "fsr1_easu_common.cuh"
 
 namespace fsr1 {
 
 constexpr int kThreads = 256;
-
-// ---- PTX wrappers: mbarrier + TMA ------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra LAB_DONE;\n"
-      "bra LAB_WAIT;\n"
-      "LAB_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(phase)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// ---- small helpers ------------------------------------------------------------------------------------
-__device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-__device__ __forceinline__ __half2 h2c(float v) { return __float2half2_rn(v); }
-__device__ __forceinline__ float rcp_approx(float a) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
 
 // Zero-filled out-of-image texels of a TMA box -> clamp-to-edge.  Sources are always in-image positions
 // (never rewritten), destinations always out-of-image ones (never read), so no intermediate barrier.
@@ -95,37 +52,6 @@ __device__ __forceinline__ void clamp_fixup(uint2* tile, int BW, int BH, int gx0
 __device__ __forceinline__ float texel_luma(uint2 t) {  // 2*luma = 0.5 B + (0.5 R + G); exact in fp32
   const float2 rg = __half22float2(u2h2(t.x));
   return fmaf(__low2float(u2h2(t.y)), 0.5f, fmaf(rg.x, 0.5f, rg.y));
-}
-
-// FsrEasuSetF without the bilinear weight: (dirX, dirY, lenX^2 + lenY^2) of the texel whose luma is lC.
-__device__ __forceinline__ float4 texel_terms(float lA, float lB, float lC, float lD, float lE) {
-  const float dirX = lD - lB, dirY = lE - lA;
-  const float lenX = sat(fabsf(dirX) * prx_lo_rcp(fmaxf(fabsf(lD - lC), fabsf(lC - lB))));
-  const float lenY = sat(fabsf(dirY) * prx_lo_rcp(fmaxf(fabsf(lE - lC), fabsf(lC - lA))));
-  return make_float4(dirX, dirY, fmaf(lenX, lenX, lenY * lenY), 0.0f);
-}
-
-// Per-pixel filter shape from the blended (dir, len): the coefficients the tap loop needs.  fp32.
-struct Shape { float qa, qb, qc, lob, clp; };
-__device__ __forceinline__ Shape pixel_shape(float dx, float dy, float len) {
-  const float dirR = fmaf(dx, dx, dy * dy);
-  const bool zro = dirR < (1.0f / 32768.0f);
-  const float rs = zro ? 1.0f : prx_lo_rsq(dirR);
-  dx = (zro ? 1.0f : dx) * rs;
-  dy *= rs;
-  len *= 0.5f;
-  len *= len;
-  const float dx2 = dx * dx, dy2 = dy * dy;
-  const float stretch = (dx2 + dy2) * prx_lo_rcp(fmaxf(fabsf(dx), fabsf(dy)));
-  const float l2x = fmaf(stretch - 1.0f, len, 1.0f), l2y = fmaf(-0.5f, len, 1.0f);
-  Shape s;
-  s.lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
-  s.clp = prx_lo_rcp(s.lob);
-  const float X2 = l2x * l2x, Y2 = l2y * l2y;
-  s.qa = fmaf(X2, dx2, Y2 * dy2);
-  s.qc = fmaf(X2, dy2, Y2 * dx2);
-  s.qb = (dx * dy * 2.0f) * (X2 - Y2);
-  return s;
 }
 
 // window weight of (up to) two pixels at squared distance d2
@@ -485,24 +411,6 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 // one RGBA16F texel = one 64-bit TMA element; tensor = the stored window of the image
 static bool make_tmap(CUtensorMap* tmap, const ImgView& in, int BW, int BH) {
   EncodeTiledFn encode = get_encode_fn();
@@ -514,13 +422,6 @@ static bool make_tmap(CUtensorMap* tmap, const ImgView& in, int BW, int BH) {
   return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// Same float arithmetic as easu_pos on the device.
-static inline int host_fp(int o, float scale, float offset) {
-  volatile float m = (float)o * scale;
-  volatile float s = m + offset;
-  return (int)floorf(s);
 }
 
 // Largest footprint (in texels) any tile of `tile` output pixels needs along one axis; with even_origin the
@@ -535,16 +436,6 @@ static int max_footprint(int n_out, int first, int tile, float scale, float offs
     if (span > best) best = span;
   }
   return best;
-}
-
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
 }
 
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name) {

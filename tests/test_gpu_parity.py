@@ -77,9 +77,15 @@ def test_fp32_default_within_1e5(shape, gen):
     src = getattr(F, gen)(iw, ih, 32)
     want = ol.easu(src, ow, oh)
     got = gpu_easu(src, ow, oh)
+    if (2 * iw, 2 * ih) == (ow, oh):
+        assert api.last_kernel().startswith("easu_f32_quad2x"), api.last_kernel()
     assert np.abs(got - want).max() <= TOL32
-    r = gpu_rcas(want, 0.25)
-    assert np.abs(r - ol.rcas(want, ol.rcas_con(0.25))).max() <= TOL32
+    alt = gpu_easu(src, ow, oh, api.FLAG_FORCE_DIRECT)
+    assert api.last_kernel().startswith("easu_direct<f32,fast") and np.abs(alt - want).max() <= TOL32
+    for clamp in (0, api.FLAG_RCAS_CLAMP):
+        r = gpu_rcas(want, 0.25, clamp)
+        assert api.last_kernel().startswith("rcas_f32_packed"), api.last_kernel()
+        assert np.abs(r - ol.rcas(want, ol.rcas_con(0.25), bool(clamp))).max() <= TOL32
 
 
 @pytest.mark.parametrize("shape", SHAPES)
