@@ -128,7 +128,8 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
     if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
     e = launch_easu_href(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
-    e = launch_easu_h_tiled(p, s, &name);
+    if (flags & FSR1_FLAG_PRECISE) e = launch_easu_h_precise(p, s, &name);
+    if (e == cudaErrorNotSupported) e = launch_easu_h_tiled(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_easu_f32_tiled(p, s, &name);
   }

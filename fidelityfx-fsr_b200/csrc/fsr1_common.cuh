@@ -102,6 +102,7 @@ cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cuda
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name);  // RGBA32F, exactly 2x
+cudaError_t launch_easu_h_precise(const EasuParams& p, cudaStream_t s, const char** name);  // RGBA16F io, fp32 math, 2x
 cudaError_t launch_rcas_f32_packed(const RcasParams& p, cudaStream_t s, const char** name);
 // Literal FsrEasuH / FsrRcasH semantics, bit-identical to the reference's packed-half source (parity path).
 cudaError_t launch_easu_href(const EasuParams& p, cudaStream_t s, const char** name);

@@ -13,14 +13,36 @@
 namespace fsr1 {
 
 constexpr int kFQCX = 32, kFQBW = kFQCX + 4, kFQSW = kFQBW - 2;
-template <int NW> struct FQuadCfg {
-  static constexpr int kCY = 2 * NW, kBH = kCY + 3, kSH = kBH - 2, kElems = kFQBW * kBH;
-  static constexpr int kPad = ((kElems * 16 + 127) / 128) * 128 / 16;
+
+// storage of one texel in the tile / in the images: RGBA32F (float4) or RGBA16F (uint2); arithmetic is fp32 either way
+template <typename S> struct Tex;
+template <> struct Tex<float> {
+  using T = float4;
+  static constexpr int kBytes = 16;
+  static __device__ __forceinline__ float4 rgb(const float4& t) { return t; }
+  static __device__ __forceinline__ float4 pack(const float4& c) { return c; }
 };
-template <int NW> struct __align__(128) FQuadSmem {
-  float4 tile[2][FQuadCfg<NW>::kPad];
-  float4 S[kFQSW * FQuadCfg<NW>::kSH];
-  float L[FQuadCfg<NW>::kElems];
+template <> struct Tex<__half> {
+  using T = uint2;
+  static constexpr int kBytes = 8;
+  static __device__ __forceinline__ float4 rgb(const uint2& t) {
+    const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    return make_float4(rg.x, rg.y, __low2float(*reinterpret_cast<const __half2*>(&t.y)), 1.0f);
+  }
+  static __device__ __forceinline__ uint2 pack(const float4& c) {
+    const __half2 rg = __floats2half2_rn(c.x, c.y), ba = __floats2half2_rn(c.z, 1.0f);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&ba));
+  }
+};
+
+template <typename S, int NW> struct FQuadCfg {
+  static constexpr int kCY = 2 * NW, kBH = kCY + 3, kSH = kBH - 2, kElems = kFQBW * kBH;
+  static constexpr int kPad = ((kElems * Tex<S>::kBytes + 127) / 128) * 128 / Tex<S>::kBytes;
+};
+template <typename S, int NW> struct __align__(128) FQuadSmem {
+  typename Tex<S>::T tile[2][FQuadCfg<S, NW>::kPad];
+  float4 S_[kFQSW * FQuadCfg<S, NW>::kSH];
+  float L[FQuadCfg<S, NW>::kElems];
   uint64_t bar[2];
 };
 
@@ -91,13 +113,18 @@ __device__ __forceinline__ void fquad_pair(const float4 (&t)[4][4], const ShapeR
   outB = make_float4(fminf(mx.x, fmaxf(mn.x, aB.x * rB)), fminf(mx.y, fmaxf(mn.y, aB.y * rB)), fminf(mx.z, fmaxf(mn.z, aB.z * rB)), 1.0f);
 }
 
-template <int NW, int MINB>
+template <typename S, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
                        const int n_tiles, const int mbase) {
-  using C = FQuadCfg<NW>;
-  constexpr int NT = NW * 32;
-  __shared__ FQuadSmem<NW> sm;
+  using C = FQuadCfg<S, NW>;
+  using TT = typename Tex<S>::T;
+  constexpr int NT = NW * 32, kB = Tex<S>::kBytes;
+  __shared__ FQuadSmem<S, NW> sm;
+  auto load_box = [&](TT* dst, int x, int y, uint64_t* bar) {
+    if (kB == 16) tma_load_3d(dst, &tmap, 0, x, y, bar);
+    else tma_load_2d(dst, &tmap, x, y, bar);
+  };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -109,18 +136,18 @@ easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap t
   auto box_y = [&](int t) { return mbase + (t / tiles_x) * C::kCY - 1; };
   int t = blockIdx.x;
   if (tid == 0 && t < n_tiles) {
-    mbar_expect_tx(&sm.bar[0], C::kElems * 16u);
-    tma_load_3d(sm.tile[0], &tmap, 0, box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
+    mbar_expect_tx(&sm.bar[0], C::kElems * (uint32_t)kB);
+    load_box(sm.tile[0], box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
   }
   for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
     const int b = it & 1;
     const int tn = t + gridDim.x;
     if (tid == 0 && tn < n_tiles) {
       fence_proxy_async();
-      mbar_expect_tx(&sm.bar[b ^ 1], C::kElems * 16u);
-      tma_load_3d(sm.tile[b ^ 1], &tmap, 0, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
+      mbar_expect_tx(&sm.bar[b ^ 1], C::kElems * (uint32_t)kB);
+      load_box(sm.tile[b ^ 1], box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
     }
-    float4* tile = sm.tile[b];
+    TT* tile = sm.tile[b];
     const int gx0 = box_x(t), gy0 = box_y(t);
     mbar_wait(&sm.bar[b], (it >> 1) & 1);
     if (gx0 < 0 || gy0 < 0 || gx0 + kFQBW > p.in.w || gy0 + C::kBH > p.in.h) {  // clamp-to-edge fix-up
@@ -135,14 +162,14 @@ easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap t
       __syncthreads();
     }
     for (int i = tid; i < C::kElems; i += NT) {
-      const float4 c = tile[i];
+      const float4 c = Tex<S>::rgb(tile[i]);
       sm.L[i] = fmaf(c.z, 0.5f, fmaf(c.x, 0.5f, c.y));
     }
     __syncthreads();
     for (int idx = tid; idx < kFQSW * C::kSH; idx += NT) {
       const int j = idx / kFQSW, i = idx - j * kFQSW;
       const float* c = sm.L + (j + 1) * kFQBW + (i + 1);
-      sm.S[idx] = texel_terms(c[-kFQBW], c[-1], c[0], c[1], c[kFQBW]);
+      sm.S_[idx] = texel_terms(c[-kFQBW], c[-1], c[0], c[1], c[kFQBW]);
     }
     __syncthreads();
 
@@ -154,13 +181,13 @@ easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap t
       const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
       if (oxA >= p.out.w || !(rowT || rowB)) continue;
       float4 tp[4][4];
-      const float4* t0 = tile + r * kFQBW + lane;
+      const TT* t0 = tile + r * kFQBW + lane;
 #pragma unroll
       for (int R = 0; R < 4; R++)
 #pragma unroll
         for (int K = 0; K < 4; K++)
-          if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kFQBW + K];
-      const float4* s0 = sm.S + r * kFQSW + lane;
+          if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = Tex<S>::rgb(t0[R * kFQBW + K]);
+      const float4* s0 = sm.S_ + r * kFQSW + lane;
       const float4 f = s0[0], g = s0[1], j = s0[kFQSW], k = s0[kFQSW + 1];
       const float3 mn = make_float3(fminf(fminf(tp[1][1].x, tp[1][2].x), fminf(tp[2][1].x, tp[2][2].x)),
                                     fminf(fminf(tp[1][1].y, tp[1][2].y), fminf(tp[2][1].y, tp[2][2].y)),
@@ -173,50 +200,68 @@ easu_f32_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap t
         return pixel_shape_rot(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))), fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
                            fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
       };
-      unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 16;
+      unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * kB;
       const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
       float4 oA, oB;
       if (rowT) {
         fquad_pair<false>(tp, blend(0.5625f, 0.1875f, 0.1875f, 0.0625f), blend(0.1875f, 0.5625f, 0.0625f, 0.1875f), mn, mx, oA, oB);
-        if (okA) *reinterpret_cast<float4*>(orow) = oA;
-        if (okB) *reinterpret_cast<float4*>(orow + 16) = oB;
+        if (okA) *reinterpret_cast<TT*>(orow) = Tex<S>::pack(oA);
+        if (okB) *reinterpret_cast<TT*>(orow + kB) = Tex<S>::pack(oB);
       }
       if (rowB) {
         fquad_pair<true>(tp, blend(0.1875f, 0.0625f, 0.5625f, 0.1875f), blend(0.0625f, 0.1875f, 0.1875f, 0.5625f), mn, mx, oA, oB);
-        if (okA) *reinterpret_cast<float4*>(orow + p.out.pitch) = oA;
-        if (okB) *reinterpret_cast<float4*>(orow + p.out.pitch + 16) = oB;
+        if (okA) *reinterpret_cast<TT*>(orow + p.out.pitch) = Tex<S>::pack(oA);
+        if (okB) *reinterpret_cast<TT*>(orow + p.out.pitch + kB) = Tex<S>::pack(oB);
       }
     }
     __syncthreads();
   }
 }
 
-cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name) {
+template <typename S>
+static cudaError_t launch_quad_f32math(const EasuParams& p, cudaStream_t s, const char** name, const char* nm) {
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
   if (!(p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f)) return cudaErrorNotSupported;  // 2x only
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return cudaErrorNotSupported;
-  constexpr int NW = 4;
-  using C = FQuadCfg<NW>;
+  constexpr int NW = 4, per_sm = 4;
+  using C = FQuadCfg<S, NW>;
   CUtensorMap tmap;
-  const cuuint64_t dims[3] = {4, (cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
-  const cuuint64_t strides[2] = {16, (cuuint64_t)p.in.pitch};
-  const cuuint32_t box[3] = {4, (cuuint32_t)kFQBW, (cuuint32_t)C::kBH};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return cudaErrorNotSupported;
+  CUresult r;
+  if (Tex<S>::kBytes == 16) {
+    const cuuint64_t dims[3] = {4, (cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
+    const cuuint64_t strides[2] = {16, (cuuint64_t)p.in.pitch};
+    const cuuint32_t box[3] = {4, (cuuint32_t)kFQBW, (cuuint32_t)C::kBH};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.in.pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)kFQBW, (cuuint32_t)C::kBH};
+    const cuuint32_t estr[2] = {1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, p.in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
   const int k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
   const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
   const int tiles_x = (k_last + 1 + 1 + kFQCX - 1) / kFQCX, tiles_y = (m_last - m_first + 1 + C::kCY - 1) / C::kCY;
   const int n_tiles = tiles_x * tiles_y;
-  const int per_sm = 4;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
-  easu_f32_quad2x_kernel<NW, per_sm><<<grid, NW * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
-  *name = "easu_f32_quad2x<4w,4/sm,tma2,ffma2>";
+  easu_f32_quad2x_kernel<S, NW, per_sm><<<grid, NW * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+  *name = nm;
   return cudaGetLastError();
+}
+
+cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name) {
+  return launch_quad_f32math<float>(p, s, name, "easu_f32_quad2x<4w,4/sm,tma2,ffma2>");
+}
+// RGBA16F storage, fp32 arithmetic (FSR1_FLAG_PRECISE): the accuracy of the fp32 path at fp16 bandwidth
+cudaError_t launch_easu_h_precise(const EasuParams& p, cudaStream_t s, const char** name) {
+  return launch_quad_f32math<__half>(p, s, name, "easu_h16io_f32math_quad2x<4w,4/sm,tma2,ffma2>");
 }
 
 }  // namespace fsr1

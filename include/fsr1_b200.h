@@ -60,6 +60,8 @@ enum {
                                        to the reference source compiled with -ffp-contract=off          */
   FSR1_FLAG_FORCE_DIRECT = 1u << 2, /* skip the TMA/shared-memory kernels, use the direct-load kernels   */
   FSR1_FLAG_NO_RCAS = 1u << 3,      /* fsr1_upscale*: EASU straight to the output (bUseRcas == false)   */
+  FSR1_FLAG_PRECISE = 1u << 5,      /* fp16 images: fp32 arithmetic on fp16 storage where a tiled kernel exists for it
+                                       (EASU at exactly 2x: packed FFMA2 taps); ~10x closer to the fp32 algorithm */
   FSR1_FLAG_H_REFERENCE = 1u << 4   /* fp16 images only: the literal FsrEasuH / FsrRcasH arithmetic (packed-half
                                        algorithm, half magic numbers, per-operation half rounding), bit-identical
                                        to the reference's H source; a parity path, slower and LESS accurate than

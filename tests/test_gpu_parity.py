@@ -155,15 +155,27 @@ def test_h_reference_mode_against_golden_vectors():
             assert np.array_equal(r.view(np.uint16), G[key])
 
 
-def e2e_check(got, want, what):
-    """End to end (EASU -> fp16 intermediate -> RCAS) against the fp32 oracle end to end.  RCAS amplifies any
-    difference in its input by up to 1/(1+4*lobe) + ... ~ 4-7x, so the per-kernel bound (1e-2 each, asserted in the
-    per-stage tests) does not compose into 1e-2 end to end; what is asserted here is what was measured with margin:
-    max <= 2.5e-2, fewer than 1 pixel in 10^4 beyond 1e-2, mean <= 1.5e-3 (DESIGN.md "numerics")."""
+def test_precise_flag_fp32_math_on_fp16_storage():
+    """FSR1_FLAG_PRECISE at 2x: packed-FFMA2 fp32 arithmetic on RGBA16F images; only the final rounding to half is left."""
+    for gen in ("uniform", "structured"):
+        iw, ih, ow, oh = 200, 120, 400, 240
+        src = F.to_half(getattr(F, gen)(iw, ih, 35))
+        want = ol.easu(src.astype(np.float32), ow, oh)
+        got = gpu_easu(src, ow, oh, api.FLAG_PRECISE)
+        assert api.last_kernel().startswith("easu_h16io_f32math"), api.last_kernel()
+        assert np.abs(got.astype(np.float32) - want).max() <= 6e-4      # half ulp at 1.0 is 4.9e-4
+        assert np.all(got[..., 3] == 1.0)
+        mid = gpu_rcas(got, 0.25)
+        e2e_check(mid, ol.rcas(want, ol.rcas_con(0.25)), ("precise", gen), tight=True)
+
+
+def e2e_check(got, want, what, tight=False):
+    """End to end (EASU -> fp16 intermediate -> RCAS) against the fp32 oracle end to end: max-abs <= 1e-2.
+    RCAS amplifies differences in its input 4-7x, so this is the demanding check; measured at 4K: 6.4e-3 max,
+    4e-4 mean (DESIGN.md "numerics").  tight = the FSR1_FLAG_PRECISE path, held to 4e-3."""
     d = np.abs(got.astype(np.float32) - want)[..., :3]
-    assert d.max() <= 2.5e-2, (what, d.max())
-    assert (d > 1e-2).mean() <= 1e-4, (what, (d > 1e-2).mean())
-    assert d.mean() <= 1.5e-3, (what, d.mean())
+    assert d.max() <= (4e-3 if tight else TOL16), (what, d.max())
+    assert d.mean() <= 1e-3, (what, d.mean())
 
 
 def test_end_to_end_fp16_pipeline():

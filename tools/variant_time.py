@@ -27,13 +27,16 @@ def timeit(fn, n=200):
     for i in range(n): fn(i)
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
-te = timeit(lambda i: api.easu(ins[i % R], tmps[i % R], econ)); ke = api.last_kernel()
+EF = int(os.environ.get("FSR1_TEST_EASU_FLAGS", "0"))
+te = timeit(lambda i: api.easu(ins[i % R], tmps[i % R], econ, flags=EF)); ke = api.last_kernel()
 tr = timeit(lambda i: api.rcas(tmps[i % R], outs[i % R], rcon)); kr = api.last_kernel()
-tb = timeit(lambda i: api.upscale(ins[i % R], tmps[i % R], outs[i % R], econ, rcon))
+tb = timeit(lambda i: api.upscale(ins[i % R], tmps[i % R], outs[i % R], econ, rcon, flags=EF))
 src = ins[0].cpu().numpy()
 e_want = ol.easu(np.ascontiguousarray(src).astype(np.float32), ow, oh)
 e_got = tmps[0].cpu().numpy()
 r_want = ol.rcas(e_got.astype(np.float32), ol.rcas_con(0.25))
+e2e = ol.rcas(e_want, ol.rcas_con(0.25))
+print("e2e max err %.5f" % np.abs(outs[0].cpu().numpy().astype(np.float32) - e2e).max())
 print("%s | %s %.1f us | %s %.1f us | both %.1f us (%.0f Mpix/s) | err easu %.4f rcas %.4f" % (
     wl, ke, te, kr, tr, tb, ow * oh / tb, np.abs(e_got.astype(np.float32) - e_want).max(),
     np.abs(outs[0].cpu().numpy().astype(np.float32) - r_want).max()))
