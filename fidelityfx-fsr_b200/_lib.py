@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfsr1_b200.so")
 FSR1_OK = 0
 FORMAT_RGBA16F, FORMAT_RGBA32F = 1, 2
 FLAG_RCAS_CLAMP, FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_H_REFERENCE, FLAG_PRECISE = 1, 2, 4, 8, 16, 32
+FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA = 64, 128
 
 # every symbol include/fsr1_b200.h declares
 SYMBOLS = ["fsr1_easu", "fsr1_rcas", "fsr1_easu_input_rows", "fsr1_upscale", "fsr1_context_create",

@@ -160,6 +160,7 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   p.sharp_h2 = con[1];
   p.y0 = (int)y0; p.y1 = (int)y1;
   p.clamp = (flags & FSR1_FLAG_RCAS_CLAMP) ? 1 : 0;
+  p.options = ((flags & FSR1_FLAG_RCAS_DENOISE) ? 1 : 0) | ((flags & FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA) ? 2 : 0);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
   cudaError_t e = cudaErrorNotSupported;
@@ -167,6 +168,9 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   if (flags & FSR1_FLAG_H_REFERENCE) {
     if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
     e = launch_rcas_href(p, s, &name);
+  } else if (p.options) {
+    // the reference's optional RCAS variants run on the direct kernels (fp32 arithmetic); the packed kernels
+    // implement the configuration the sample ships (neither macro defined)
   } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_rcas_h_packed(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {

@@ -27,6 +27,7 @@ struct RcasParams {
   uint32_t sharp_h2;  // con.y: half2(sharp,sharp)
   int y0, y1;
   int clamp;        // 0: out-of-image taps read 0 (D3D12 Load), 1: clamp
+  int options;      // bit 0: FSR_RCAS_DENOISE, bit 1: FSR_RCAS_PASSTHROUGH_ALPHA (direct / H-reference kernels)
 };
 
 // ---- the reference's bit-trick approximations (ffx-fsr/ffx_a.h:1843-1845), bit-exact ------------
@@ -71,8 +72,11 @@ template <> struct Px<float> {
     const float4 v = __ldg(reinterpret_cast<const float4*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
     return make_float3(v.x, v.y, v.z);
   }
-  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b) {
-    reinterpret_cast<float4*>(im.base + (long long)(y - im.row0) * im.pitch)[x] = make_float4(r, g, b, 1.0f);
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b, float a = 1.0f) {
+    reinterpret_cast<float4*>(im.base + (long long)(y - im.row0) * im.pitch)[x] = make_float4(r, g, b, a);
+  }
+  static __device__ __forceinline__ float alpha(const ImgView& im, int x, int y) {
+    return __ldg(reinterpret_cast<const float4*>(im.base + (long long)(y - im.row0) * im.pitch) + x).w;
   }
 };
 template <> struct Px<__half> {
@@ -83,8 +87,12 @@ template <> struct Px<__half> {
     const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
     return make_float3(rg.x, rg.y, ba.x);
   }
-  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b) {
-    __half2 rg = __floats2half2_rn(r, g), ba = __floats2half2_rn(b, 1.0f);
+  static __device__ __forceinline__ float alpha(const ImgView& im, int x, int y) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return __high2float(*reinterpret_cast<const __half2*>(&v.y));
+  }
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b, float a = 1.0f) {
+    __half2 rg = __floats2half2_rn(r, g), ba = __floats2half2_rn(b, a);
     uint2 v;
     v.x = *reinterpret_cast<uint32_t*>(&rg);
     v.y = *reinterpret_cast<uint32_t*>(&ba);

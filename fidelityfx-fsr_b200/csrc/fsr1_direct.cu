@@ -58,7 +58,6 @@ __device__ __forceinline__ void easu_tap(float3& aC, float& aW, float ox, float 
   aW = A::add(aW, w);
 }
 
-__device__ __forceinline__ float luma2(float3 c, bool) { return 0.f; }
 template <bool kExact> __device__ __forceinline__ float luma(float3 c) {
   using A = Ar<kExact>;
   return A::add(A::mul(c.z, 0.5f), A::add(A::mul(c.x, 0.5f), c.y));  // 2*luma = 0.5B + (0.5R + G)
@@ -177,14 +176,25 @@ __global__ void __launch_bounds__(256) rcas_direct_kernel(const RcasParams p) {
   const float lR = rcas_lobe<kExact>(b.x, d.x, e.x, f.x, h.x);
   const float lG = rcas_lobe<kExact>(b.y, d.y, e.y, f.y, h.y);
   const float lB = rcas_lobe<kExact>(b.z, d.z, e.z, f.z, h.z);
-  const float lobe = A::mul(fmaxf(-0.1875f, fminf(fmaxf(lR, fmaxf(lG, lB)), 0.0f)), p.sharp);
+  float lobe = A::mul(fmaxf(-0.1875f, fminf(fmaxf(lR, fmaxf(lG, lB)), 0.0f)), p.sharp);
+  if (p.options & 1) {  // FSR_RCAS_DENOISE (ffx_fsr1.h:731-739, 761-763)
+    const float bL = luma<kExact>(b), dL = luma<kExact>(d), eL = luma<kExact>(e), fL = luma<kExact>(f), hL = luma<kExact>(h);
+    float nz = A::sub(A::mad(0.25f, hL, A::mad(0.25f, fL, A::mad(0.25f, dL, A::mul(0.25f, bL)))), eL);
+    const float mx = fmaxf(fmaxf(bL, fmaxf(dL, eL)), fmaxf(fL, hL)), mn = fminf(fminf(bL, fminf(dL, eL)), fminf(fL, hL));
+    const float rng = A::sub(mx, mn);
+    const float sd = __uint_as_float(0x7ef19fffu - __float_as_uint(rng));
+    nz = sat(A::mul(fabsf(nz), A::mul(sd, A::mad(-sd, rng, 2.0f))));
+    nz = A::mad(-0.5f, nz, 1.0f);
+    lobe = A::mul(lobe, nz);
+  }
   // APrxMedRcpF1 (ffx_a.h:1844): bit-trick seed + one Newton step
   const float a = A::mad(4.0f, lobe, 1.0f);
   const float s = __uint_as_float(0x7ef19fffu - __float_as_uint(a));
   const float rcpL = A::mul(s, A::mad(-s, a, 2.0f));
+  const float alpha = (p.options & 2) ? Px<S>::alpha(p.in, x, y) : 1.0f;  // FSR_RCAS_PASSTHROUGH_ALPHA (:688-702)
   Px<S>::store(p.out, x, y, rcas_resolve<kExact>(lobe, rcpL, b.x, d.x, e.x, f.x, h.x),
                rcas_resolve<kExact>(lobe, rcpL, b.y, d.y, e.y, f.y, h.y),
-               rcas_resolve<kExact>(lobe, rcpL, b.z, d.z, e.z, f.z, h.z));
+               rcas_resolve<kExact>(lobe, rcpL, b.z, d.z, e.z, f.z, h.z), alpha);
 }
 
 static inline dim3 grid_for(int w, int rows) { return dim3((w + 31) / 32, (rows + 7) / 8, 1); }

@@ -40,10 +40,10 @@ __device__ __forceinline__ H3 load_h3(const ImgView& im, int x, int y) {
   const uint2 v = __ldg(reinterpret_cast<const uint2*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
   return H3{hbits((unsigned short)(v.x & 0xffffu)), hbits((unsigned short)(v.x >> 16)), hbits((unsigned short)(v.y & 0xffffu))};
 }
-__device__ __forceinline__ void store_h3(const ImgView& im, int x, int y, H r, H g, H b) {
+__device__ __forceinline__ void store_h3(const ImgView& im, int x, int y, H r, H g, H b, unsigned short a = 0x3c00) {
   uint2 v;
   v.x = (uint32_t)bitsh(r) | ((uint32_t)bitsh(g) << 16);
-  v.y = (uint32_t)bitsh(b) | (0x3c00u << 16);
+  v.y = (uint32_t)bitsh(b) | ((uint32_t)a << 16);
   reinterpret_cast<uint2*>(im.base + (long long)(y - im.row0) * im.pitch)[x] = v;
 }
 
@@ -181,10 +181,23 @@ __global__ void __launch_bounds__(256) rcas_href_kernel(const RcasParams p) {
   const H3 f = rcas_fetch_h(p, x + 1, y), h = rcas_fetch_h(p, x, y + 1);
   const H lR = lobe_h(b.r, d.r, e.r, f.r, h.r), lG = lobe_h(b.g, d.g, e.g, f.g, h.g), lB = lobe_h(b.b, d.b, e.b, f.b, h.b);
   const H sharp = hbits((unsigned short)(p.sharp_h2 & 0xffffu));  // AH2_AU1(con.y).x (ffx_fsr1.h:857)
-  const H lobe = hmax_(hf(-0.1875f), hmin_(hmax_(lR, hmax_(lG, lB)), hf(0.0f))) * sharp;
+  H lobe = hmax_(hf(-0.1875f), hmin_(hmax_(lR, hmax_(lG, lB)), hf(0.0f))) * sharp;
+  if (p.options & 1) {  // FSR_RCAS_DENOISE (ffx_fsr1.h:829-837, 859-861)
+    const H hh = hf(0.5f), q = hf(0.25f);
+    const H bL = b.b * hh + (b.r * hh + b.g), dL = d.b * hh + (d.r * hh + d.g), eL = e.b * hh + (e.r * hh + e.g);
+    const H fL = f.b * hh + (f.r * hh + f.g), hL = h.b * hh + (h.r * hh + h.g);
+    H nz = q * bL + q * dL + q * fL + q * hL - eL;
+    const H mx = hmax_(hmax_(bL, hmax_(dL, eL)), hmax_(fL, hL)), mn = hmin_(hmin_(bL, hmin_(dL, eL)), hmin_(fL, hL));
+    nz = hsat_(habs_(nz) * prx_med_rcp_hh(mx - mn));
+    nz = hf(-0.5f) * nz + hf(1.0f);
+    lobe = lobe * nz;
+  }
   const H rcpL = prx_med_rcp_hh(hf(4.0f) * lobe + hf(1.0f));
+  unsigned short alpha = 0x3c00;
+  if (p.options & 2)  // FSR_RCAS_PASSTHROUGH_ALPHA (:786-800): centre texel's alpha
+    alpha = (unsigned short)(__ldg(reinterpret_cast<const uint2*>(p.in.base + (long long)(y - p.in.row0) * p.in.pitch) + x).y >> 16);
   store_h3(p.out, x, y, resolve_h(lobe, rcpL, b.r, d.r, e.r, f.r, h.r), resolve_h(lobe, rcpL, b.g, d.g, e.g, f.g, h.g),
-           resolve_h(lobe, rcpL, b.b, d.b, e.b, f.b, h.b));
+           resolve_h(lobe, rcpL, b.b, d.b, e.b, f.b, h.b), alpha);
 }
 
 cudaError_t launch_easu_href(const EasuParams& p, cudaStream_t s, const char** name) {

@@ -62,6 +62,8 @@ enum {
   FSR1_FLAG_NO_RCAS = 1u << 3,      /* fsr1_upscale*: EASU straight to the output (bUseRcas == false)   */
   FSR1_FLAG_PRECISE = 1u << 5,      /* fp16 images: fp32 arithmetic on fp16 storage where a tiled kernel exists for it
                                        (EASU at exactly 2x: packed FFMA2 taps); ~10x closer to the fp32 algorithm */
+  FSR1_FLAG_RCAS_DENOISE = 1u << 6, /* the reference's FSR_RCAS_DENOISE compile-time option (ffx_fsr1.h:651,731-763)      */
+  FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA = 1u << 7, /* FSR_RCAS_PASSTHROUGH_ALPHA (:648,688-702): output alpha = input alpha */
   FSR1_FLAG_H_REFERENCE = 1u << 4   /* fp16 images only: the literal FsrEasuH / FsrRcasH arithmetic (packed-half
                                        algorithm, half magic numbers, per-operation half rounding), bit-identical
                                        to the reference's H source; a parity path, slower and LESS accurate than

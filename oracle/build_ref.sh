@@ -34,5 +34,14 @@ else
   head -30 "$TMP/half.err" >&2
   g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o "$TMP/ref_driver.o"
 fi
-g++ -shared -fopenmp -o "$OUT/libfsr1_ref.so" "$TMP/ref_driver.o" "$TMP/ref_cpu.o" -lm
+# the reference's compile-time RCAS options (ffx_fsr1.h:647-651), each as its own namespaced variant
+VARIANTS=""
+HALFFLAGS=""
+if [ ! -s "$TMP/half.err" ]; then HALFFLAGS="-DFSR1_REF_HALF -fexcess-precision=16"; fi
+for v in "dn:-DFSR_RCAS_DENOISE=1" "pa:-DFSR_RCAS_PASSTHROUGH_ALPHA=1" "dnpa:-DFSR_RCAS_DENOISE=1 -DFSR_RCAS_PASSTHROUGH_ALPHA=1"; do
+  tag="${v%%:*}"; defs="${v#*:}"
+  g++ $CXXFLAGS $HALFFLAGS $defs -DREFNS=fsr1ref_$tag -DREFSUF=_$tag -c "$HERE/ref_driver.cpp" -o "$TMP/ref_driver_$tag.o"
+  VARIANTS="$VARIANTS $TMP/ref_driver_$tag.o"
+done
+g++ -shared -fopenmp -o "$OUT/libfsr1_ref.so" "$TMP/ref_driver.o" $VARIANTS "$TMP/ref_cpu.o" -lm
 echo "build_ref: wrote $OUT/libfsr1_ref.so"

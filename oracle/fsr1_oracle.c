@@ -169,20 +169,21 @@ void fsr1o_easu_f32(const float* in, int inW, int inH, size_t inPitch, float* ou
   }
 }
 
-void fsr1o_rcas_f32(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
-                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+/* options: bit 0 = FSR_RCAS_DENOISE (ffx_fsr1.h:731-739,761-763), bit 1 = FSR_RCAS_PASSTHROUGH_ALPHA (:688-702) */
+void fsr1o_rcas_f32_opt(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
+                        const uint32_t* con, int oob_clamp, int y0, int y1, int options) {
   float sharp = u2f(con[0]);
 #pragma omp parallel for schedule(static)
   for (int y = y0; y < y1; y++) {
     for (int x = 0; x < W; x++) {
       static const int ox[5] = {0, -1, 0, 1, 0}, oy[5] = {-1, 0, 0, 0, 1}; /* b d e f h */
-      float t[5][3];
+      float t[5][4];
       for (int i = 0; i < 5; i++) {
         int sx = x + ox[i], sy = y + oy[i];
         if (oob_clamp) { sx = clampi(sx, 0, W - 1); sy = clampi(sy, 0, H - 1); }
-        if (sx < 0 || sy < 0 || sx >= W || sy >= H) { t[i][0] = t[i][1] = t[i][2] = 0.0f; continue; }
+        if (sx < 0 || sy < 0 || sx >= W || sy >= H) { t[i][0] = t[i][1] = t[i][2] = t[i][3] = 0.0f; continue; }
         const float* s = in + (size_t)sy * inPitch + (size_t)sx * 4;
-        t[i][0] = s[0]; t[i][1] = s[1]; t[i][2] = s[2];
+        t[i][0] = s[0]; t[i][1] = s[1]; t[i][2] = s[2]; t[i][3] = s[3];
       }
       float lobeC[3];
       for (int k = 0; k < 3; k++) {
@@ -194,13 +195,28 @@ void fsr1o_rcas_f32(const float* in, int W, int H, size_t inPitch, float* out, s
         lobeC[k] = fmaxf(-hitMin, hitMax);
       }
       float lobe = fmaxf(-(float)(0.25 - (1.0 / 16.0)), fminf(fmaxf(lobeC[0], fmaxf(lobeC[1], lobeC[2])), 0.0f)) * sharp;
+      if (options & 1) {
+        float L[5];
+        for (int i = 0; i < 5; i++) L[i] = t[i][2] * 0.5f + (t[i][0] * 0.5f + t[i][1]);
+        float bL = L[0], dL = L[1], eL = L[2], fL = L[3], hL = L[4];
+        float nz = 0.25f * bL + 0.25f * dL + 0.25f * fL + 0.25f * hL - eL;
+        float mx = fmaxf(fmaxf(bL, fmaxf(dL, eL)), fmaxf(fL, hL));   /* AMax3F1(AMax3F1(bL,dL,eL),fL,hL) */
+        float mn = fminf(fminf(bL, fminf(dL, eL)), fminf(fL, hL));
+        nz = satf(fabsf(nz) * prx_med_rcp(mx - mn));
+        nz = -0.5f * nz + 1.0f;
+        lobe *= nz;
+      }
       float rcpL = prx_med_rcp(4.0f * lobe + 1.0f);
       float* o = out + (size_t)y * outPitch + (size_t)x * 4;
       for (int k = 0; k < 3; k++)
         o[k] = (lobe * t[0][k] + lobe * t[1][k] + lobe * t[4][k] + lobe * t[3][k] + t[2][k]) * rcpL;
-      o[3] = 1.0f;
+      o[3] = (options & 2) ? t[2][3] : 1.0f;
     }
   }
+}
+void fsr1o_rcas_f32(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
+                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+  fsr1o_rcas_f32_opt(in, W, H, inPitch, out, outPitch, con, oob_clamp, y0, y1, 0);
 }
 
 /* ------------------------------------------------------------------ packed-half path model --- */
@@ -310,20 +326,20 @@ void fsr1o_easu_h16(const uint16_t* in, int inW, int inH, size_t inPitch, uint16
   }
 }
 
-void fsr1o_rcas_h16(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
-                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+void fsr1o_rcas_h16_opt(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+                        const uint32_t* con, int oob_clamp, int y0, int y1, int options) {
   h16 sharp = w2h((uint16_t)(con[1] & 0xffffu));
 #pragma omp parallel for schedule(static)
   for (int y = y0; y < y1; y++) {
     for (int x = 0; x < W; x++) {
       static const int ox[5] = {0, -1, 0, 1, 0}, oy[5] = {-1, 0, 0, 0, 1};
-      h16 t[5][3];
+      h16 t[5][4];
       for (int i = 0; i < 5; i++) {
         int sx = x + ox[i], sy = y + oy[i];
         if (oob_clamp) { sx = clampi(sx, 0, W - 1); sy = clampi(sy, 0, H - 1); }
-        if (sx < 0 || sy < 0 || sx >= W || sy >= H) { t[i][0] = t[i][1] = t[i][2] = 0; continue; }
+        if (sx < 0 || sy < 0 || sx >= W || sy >= H) { t[i][0] = t[i][1] = t[i][2] = t[i][3] = 0; continue; }
         const uint16_t* s = in + (size_t)sy * inPitch + (size_t)sx * 4;
-        t[i][0] = w2h(s[0]); t[i][1] = w2h(s[1]); t[i][2] = w2h(s[2]);
+        t[i][0] = w2h(s[0]); t[i][1] = w2h(s[1]); t[i][2] = w2h(s[2]); t[i][3] = w2h(s[3]);
       }
       h16 lobeC[3];
       for (int k = 0; k < 3; k++) {
@@ -335,13 +351,28 @@ void fsr1o_rcas_h16(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* 
         lobeC[k] = hmax(-hitMin, hitMax);
       }
       h16 lobe = hmax((h16)(-(0.25 - (1.0 / 16.0))), hmin(hmax(lobeC[0], hmax(lobeC[1], lobeC[2])), (h16)0.0)) * sharp;
+      if (options & 1) {
+        h16 L[5];
+        for (int i = 0; i < 5; i++) L[i] = t[i][2] * (h16)0.5 + (t[i][0] * (h16)0.5 + t[i][1]);
+        h16 bL = L[0], dL = L[1], eL = L[2], fL = L[3], hL = L[4];
+        h16 nz = (h16)0.25 * bL + (h16)0.25 * dL + (h16)0.25 * fL + (h16)0.25 * hL - eL;
+        h16 mx = hmax(hmax(bL, hmax(dL, eL)), hmax(fL, hL));
+        h16 mn = hmin(hmin(bL, hmin(dL, eL)), hmin(fL, hL));
+        nz = hsat(habs(nz) * hprx_med_rcp(mx - mn));
+        nz = (h16)(-0.5) * nz + (h16)1.0;
+        lobe *= nz;
+      }
       h16 rcpL = hprx_med_rcp((h16)4.0 * lobe + (h16)1.0);
       uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
       for (int k = 0; k < 3; k++)
         o[k] = h2w((lobe * t[0][k] + lobe * t[1][k] + lobe * t[4][k] + lobe * t[3][k] + t[2][k]) * rcpL);
-      o[3] = 0x3c00;
+      o[3] = (options & 2) ? h2w(t[2][3]) : 0x3c00;
     }
   }
+}
+void fsr1o_rcas_h16(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+                    const uint32_t* con, int oob_clamp, int y0, int y1) {
+  fsr1o_rcas_h16_opt(in, W, H, inPitch, out, outPitch, con, oob_clamp, y0, y1, 0);
 }
 
 /* ------------------------------------------------------------------ synthetic frames --------- */

@@ -14,6 +14,22 @@
 //   store float4(c,1)                sample/src/DX12/FSR_Pass.hlsl:80,86,95,101
 #include "hlsl_on_cpp.h"
 
+// Variants: the RCAS compile-time options of the reference (ffx-fsr/ffx_fsr1.h:647-651) are selected with
+//   -DFSR_RCAS_DENOISE=1 and/or -DFSR_RCAS_PASSTHROUGH_ALPHA=1, together with -DREFNS=<namespace> -DREFSUF=<suffix>;
+// each variant lives in its own namespace and exports only fsr1ref_rcas_f<suffix> / fsr1ref_rcas_h<suffix>.
+#ifndef REFNS
+#define REFNS fsr1ref_base
+#define REF_BASE 1
+#endif
+#ifndef REFSUF
+#define REFSUF
+#endif
+#define REF_CAT2(a, b) a##b
+#define REF_CAT(a, b) REF_CAT2(a, b)
+#define REF_NAME(n) REF_CAT(n, REFSUF)
+
+namespace REFNS {
+
 #define A_GPU 1
 #define A_HLSL 1
 #ifdef FSR1_REF_HALF
@@ -82,8 +98,12 @@ void FsrRcasInputH(AH1& r, AH1& g, AH1& b) {}
 
 #include "ffx_fsr1.h"  // rewritten copy
 
+}  // namespace REFNS
+using namespace REFNS;
+
 extern "C" {
 
+#ifdef REF_BASE
 // Constants as the reference computes them in its A_GPU build (FsrRcasCon's packed half uses
 // round-to-nearest f32tof16 here; the A_CPU build truncates — see ref_cpu.c for that one).
 void fsr1ref_gpu_easu_con(uint32_t* con /*16*/, float inVpW, float inVpH, float inW, float inH, float outW, float outH) {
@@ -113,24 +133,31 @@ void fsr1ref_easu_f(const float* in, int inW, int inH, size_t inPitch, float* ou
   }
 }
 
+#endif  // REF_BASE
+
 // RCAS fp32 over rows [y0,y1); oob_clamp=0 -> D3D12 Load semantics (OOB reads 0), 1 -> clamp.
-void fsr1ref_rcas_f(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
+void REF_NAME(fsr1ref_rcas_f)(const float* in, int W, int H, size_t inPitch, float* out, size_t outPitch,
                     const uint32_t* con, int oob_clamp, int y0, int y1) {
   AU4 c(con[0], con[1], con[2], con[3]);
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = y0; y < y1; y++) {
     g_f = ImgF{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
     for (int x = 0; x < W; x++) {
-      AF1 r, g, b;
+      AF1 r, g, b, a = 1.0f;
+#ifdef FSR_RCAS_PASSTHROUGH_ALPHA
+      FsrRcasF(r, g, b, a, AU2((uint)x, (uint)y), c);
+#else
       FsrRcasF(r, g, b, AU2((uint)x, (uint)y), c);
+#endif
       float* o = out + (size_t)y * outPitch + (size_t)x * 4;
-      o[0] = r; o[1] = g; o[2] = b; o[3] = 1.0f;
+      o[0] = r; o[1] = g; o[2] = b; o[3] = a;
     }
   }
 }
 
 #ifdef FSR1_REF_HALF
 // The packed-half variants: images are RGBA16F (raw half bits), pitches in halves.
+#ifdef REF_BASE
 void fsr1ref_easu_h(const uint16_t* in, int inW, int inH, size_t inPitch, uint16_t* out, int outW, int outH,
                     size_t outPitch, const uint32_t* con, int y0, int y1) {
   AU4 c0(con[0], con[1], con[2], con[3]), c1(con[4], con[5], con[6], con[7]);
@@ -146,23 +173,32 @@ void fsr1ref_easu_h(const uint16_t* in, int inW, int inH, size_t inPitch, uint16
     }
   }
 }
-void fsr1ref_rcas_h(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+#endif  // REF_BASE
+void REF_NAME(fsr1ref_rcas_h)(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
                     const uint32_t* con, int oob_clamp, int y0, int y1) {
   AU4 c(con[0], con[1], con[2], con[3]);
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = y0; y < y1; y++) {
     g_h = ImgH{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
     for (int x = 0; x < W; x++) {
-      AH1 r, g, b;
+      AH1 r, g, b, a = (AH1)1.0;
+#ifdef FSR_RCAS_PASSTHROUGH_ALPHA
+      FsrRcasH(r, g, b, a, AU2((uint)x, (uint)y), c);
+#else
       FsrRcasH(r, g, b, AU2((uint)x, (uint)y), c);
+#endif
       uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
-      o[0] = h_to_bits(r); o[1] = h_to_bits(g); o[2] = h_to_bits(b); o[3] = 0x3c00;
+      o[0] = h_to_bits(r); o[1] = h_to_bits(g); o[2] = h_to_bits(b); o[3] = h_to_bits(a);
     }
   }
 }
+#ifdef REF_BASE
 int fsr1ref_has_half(void) { return 1; }
+#endif
 #else
+#ifdef REF_BASE
 int fsr1ref_has_half(void) { return 0; }
+#endif
 #endif
 
 }  // extern "C"

@@ -101,15 +101,18 @@ def easu(img, ow, oh, con=None, y0=0, y1=None, lib=None):
     return out.view(np.float16) if half else out
 
 
-def rcas(img, con, clamp=False, y0=0, y1=None, lib=None):
+def rcas(img, con, clamp=False, y0=0, y1=None, lib=None, denoise=False, alpha=False):
+    """RCAS; denoise / alpha = the reference's compile-time options FSR_RCAS_DENOISE / FSR_RCAS_PASSTHROUGH_ALPHA."""
     lib = lib or oracle()
     h, w = img.shape[:2]
     y1 = h if y1 is None else y1
     half = img.dtype != np.float32
     src = img.view(np.uint16) if half else img
     out = np.zeros((h, w, 4), np.uint16 if half else np.float32)
-    name = {(False, True): "fsr1o_rcas_f32", (True, True): "fsr1o_rcas_h16", (False, False): "fsr1ref_rcas_f",
-            (True, False): "fsr1ref_rcas_h"}[(half, lib is oracle())]
-    getattr(lib, name)(P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con),
-                       1 if clamp else 0, y0, y1)
+    args = [P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con), 1 if clamp else 0, y0, y1]
+    if lib is oracle():
+        getattr(lib, "fsr1o_rcas_h16_opt" if half else "fsr1o_rcas_f32_opt")(*args, (1 if denoise else 0) | (2 if alpha else 0))
+    else:
+        suffix = {(False, False): "", (True, False): "_dn", (False, True): "_pa", (True, True): "_dnpa"}[(denoise, alpha)]
+        getattr(lib, ("fsr1ref_rcas_h" if half else "fsr1ref_rcas_f") + suffix)(*args)
     return out.view(np.float16) if half else out

@@ -155,6 +155,27 @@ def test_h_reference_mode_against_golden_vectors():
             assert np.array_equal(r.view(np.uint16), G[key])
 
 
+@pytest.mark.parametrize("denoise,alpha", [(True, False), (False, True), (True, True)])
+def test_rcas_denoise_and_alpha_passthrough_options(denoise, alpha):
+    """The reference's compile-time RCAS options (FSR_RCAS_DENOISE, FSR_RCAS_PASSTHROUGH_ALPHA) as run-time flags."""
+    fl = (api.FLAG_RCAS_DENOISE if denoise else 0) | (api.FLAG_RCAS_PASSTHROUGH_ALPHA if alpha else 0)
+    for gen in ("uniform", "structured"):
+        img = getattr(F, gen)(77, 45, 36)
+        for clamp in (0, api.FLAG_RCAS_CLAMP):
+            rc = ol.rcas_con(0.25)
+            want = ol.rcas(img, rc, bool(clamp), denoise=denoise, alpha=alpha)
+            got = gpu_rcas(img, 0.25, fl | clamp | api.FLAG_EXACT)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))            # fp32 exact: bit-identical
+            assert np.abs(gpu_rcas(img, 0.25, fl | clamp) - want).max() <= TOL32          # fp32 fast
+            imh = F.to_half(img)
+            goth = gpu_rcas(imh, 0.25, fl | clamp).astype(np.float32)                     # fp16 storage, fp32 math
+            assert np.abs(goth - ol.rcas(imh.astype(np.float32), rc, bool(clamp), denoise=denoise, alpha=alpha)).max() <= TOL16
+            href = gpu_rcas(imh, 0.25, fl | clamp | api.FLAG_H_REFERENCE)                 # literal FsrRcasH + options
+            assert np.array_equal(href.view(np.uint16), ol.rcas(imh, rc, bool(clamp), denoise=denoise, alpha=alpha).view(np.uint16))
+            if alpha:
+                assert np.array_equal(got[..., 3], img[..., 3]) and np.array_equal(href[..., 3], imh[..., 3])
+
+
 def test_precise_flag_fp32_math_on_fp16_storage():
     """FSR1_FLAG_PRECISE at 2x: packed-FFMA2 fp32 arithmetic on RGBA16F images; only the final rounding to half is left."""
     for gen in ("uniform", "structured"):
