@@ -232,11 +232,14 @@ def run_ours(args, rank, world, local_rank):
         total_out_px = ow * oh
         halo = 0
     else:
-        # frame = `world` slabs tall; this rank owns input rows [rank*ih, (rank+1)*ih) of it
-        H_in, H_out = ih * world, oh * world
+        # default ("weak"): the frame is `world` slabs tall, this rank owns input rows [rank*ih, (rank+1)*ih) of it;
+        # --shard-frame ("strong"): the named frame itself is cut into `world` row slabs (BASELINE configs[4] at N=8)
+        H_in, H_out = (ih, oh) if args.shard_frame else (ih * world, oh * world)
         ups = [F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev) for _ in range(RING)]
         for t, u in enumerate(ups):  # each frame's slab is resident in HBM inside its halo window
-            u.owned.copy_(torch.from_numpy(host_frame(12345 + t + 1000 * rank)).to(dev))
+            src = torch.from_numpy(host_frame(12345 + t + (0 if args.shard_frame else 1000 * rank))).to(dev)
+            o0, o1 = u.plan.owned_in_rows(rank)
+            u.owned.copy_(src[o0:o1] if args.shard_frame else src)
         if args.graph:
             for u in ups:            # halo exchange + EASU + RCAS recorded once; a step is one graph launch
                 u.capture()
@@ -321,7 +324,10 @@ def run_ours(args, rank, world, local_rank):
         traffic = load_traffic().get(kernels[dom]["kernel"])
         roofline = {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["GBps"], "peak": peak,
                     "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg[dom], "us_per_launch": kernels[dom]["us"]}
+                    "algorithmic_bytes_per_launch": alg[dom], "us_per_launch": kernels[dom]["us"],
+                    "note": "EASU is FMA-pipe-bound on B200, not HBM-bound: ~200 multiply-add-class ops per output pixel and "
+                            "HFMA2 issues at half the FFMA rate, i.e. >= 44 us per 4K frame at 100% pipe utilisation vs 12.6 us at "
+                            "the HBM roofline (ncu: profiles/r01_ncu_summary.txt, DESIGN.md section 4)"}
         path_bytes = alg["easu"] + alg["rcas"]
         kernels["path"] = {"algorithmic_bytes": path_bytes, "us": ms / K * 1e3,
                            "GBps": path_bytes / (ms / K * 1e-3) / 1e9, "frac_of_hbm_peak": path_bytes / (ms / K * 1e-3) / 1e9 / peak}
@@ -363,9 +369,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (world > 1 and args.shard_frame) else "weak", "vs_baseline": None,
             "dtype": "f16" if dts == "f16" else "f32", "data": "synthetic",
-            "config": {"workload": wl[5] if world == 1 else wl[5] + " x%d slabs tall, row-slab sharded, NCCL halo" % world,
+            "config": {"workload": wl[5] if world == 1 else wl[5] + (" cut into %d row slabs, NCCL halo" % world if args.shard_frame else " x%d slabs tall, row-slab sharded, NCCL halo" % world),
                        "sharpness_stops": SHARPNESS, "frame": "LCG uniform noise, seed 12345+t",
                        "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * ih + 2 * ow * oh) * bpp / 1e6),
                        "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step, %s" % (
@@ -410,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-4k-fp16", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")
     args = ap.parse_args()
