@@ -302,6 +302,55 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
   outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
 }
 
+// Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
+// k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
+__device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __restrict__ tile, const float4* __restrict__ S,
+                                          int gx0, int gy0, int lane, int r) {
+  const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
+    const int oyT = (gy0 + 1 + r) * 2 + 1;     // output rows 2m+1 (top pair), 2m+2 (bottom pair)
+    const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
+    if (oxA >= p.out.w || !(rowT || rowB)) return;
+    uint2 tp[4][4];
+    const uint2* t0 = tile + r * kQBW + lane;
+#pragma unroll
+    for (int R = 0; R < 4; R++)
+#pragma unroll
+      for (int K = 0; K < 4; K++)
+        if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kQBW + K];
+    const float4* s0 = S + r * kQSW + lane;
+    const float4 f = s0[0], g = s0[1], j = s0[kQSW], k = s0[kQSW + 1];
+    // de-ringing bounds of the quad: min/max of f,g,j,k per channel, broadcast to both lanes
+    const __half2 mnRG = __hmin2(__hmin2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmin2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
+    const __half2 mxRG = __hmax2(__hmax2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmax2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
+    const __half2 mnBA = __hmin2(__hmin2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmin2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
+    const __half2 mxBA = __hmax2(__hmax2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmax2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
+    const __half2 mnR = __low2half2(mnRG), mnG = __high2half2(mnRG), mnB = __low2half2(mnBA);
+    const __half2 mxR = __low2half2(mxRG), mxG = __high2half2(mxRG), mxB = __low2half2(mxBA);
+    // bilinear blends with the four constant weight sets (pp = .25/.75): horizontal first
+    const float fx = 0.75f, gx = 0.25f;
+    const float3 t25 = make_float3(fmaf(g.x, gx, f.x * fx), fmaf(g.y, gx, f.y * fx), fmaf(g.z, gx, f.z * fx));
+    const float3 t75 = make_float3(fmaf(g.x, fx, f.x * gx), fmaf(g.y, fx, f.y * gx), fmaf(g.z, fx, f.z * gx));
+    const float3 b25 = make_float3(fmaf(k.x, gx, j.x * fx), fmaf(k.y, gx, j.y * fx), fmaf(k.z, gx, j.z * fx));
+    const float3 b75 = make_float3(fmaf(k.x, fx, j.x * gx), fmaf(k.y, fx, j.y * gx), fmaf(k.z, fx, j.z * gx));
+    unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
+    const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
+    uint2 oA, oB;
+    if (rowT) {
+      const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
+      const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
+      quad_pair<false>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      if (okA) *reinterpret_cast<uint2*>(orow) = oA;
+      if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
+    }
+    if (rowB) {
+      const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
+      const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
+      quad_pair<true>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
+      if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
+    }
+}
+
 template <int NW> struct __align__(128) QuadSmem {
   uint2 tile[2][QuadCfg<NW>::kPad];
   float4 S[kQSW * QuadCfg<NW>::kSH];
@@ -362,54 +411,100 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     }
     __syncthreads();
 
-    const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
 #pragma unroll 1
-    for (int q = 0; q < 2; q++) {
-      const int r = warp + q * NW;               // cell row within the tile
-      const int oyT = (gy0 + 1 + r) * 2 + 1;     // output rows 2m+1 (top pair), 2m+2 (bottom pair)
-      const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
-      if (oxA >= p.out.w || !(rowT || rowB)) continue;
-      uint2 tp[4][4];
-      const uint2* t0 = tile + r * kQBW + lane;
-#pragma unroll
-      for (int R = 0; R < 4; R++)
-#pragma unroll
-        for (int K = 0; K < 4; K++)
-          if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kQBW + K];
-      const float4* s0 = sm.S + r * kQSW + lane;
-      const float4 f = s0[0], g = s0[1], j = s0[kQSW], k = s0[kQSW + 1];
-      // de-ringing bounds of the quad: min/max of f,g,j,k per channel, broadcast to both lanes
-      const __half2 mnRG = __hmin2(__hmin2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmin2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
-      const __half2 mxRG = __hmax2(__hmax2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmax2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
-      const __half2 mnBA = __hmin2(__hmin2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmin2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
-      const __half2 mxBA = __hmax2(__hmax2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmax2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
-      const __half2 mnR = __low2half2(mnRG), mnG = __high2half2(mnRG), mnB = __low2half2(mnBA);
-      const __half2 mxR = __low2half2(mxRG), mxG = __high2half2(mxRG), mxB = __low2half2(mxBA);
-      // bilinear blends with the four constant weight sets (pp = .25/.75): horizontal first
-      const float fx = 0.75f, gx = 0.25f;
-      const float3 t25 = make_float3(fmaf(g.x, gx, f.x * fx), fmaf(g.y, gx, f.y * fx), fmaf(g.z, gx, f.z * fx));
-      const float3 t75 = make_float3(fmaf(g.x, fx, f.x * gx), fmaf(g.y, fx, f.y * gx), fmaf(g.z, fx, f.z * gx));
-      const float3 b25 = make_float3(fmaf(k.x, gx, j.x * fx), fmaf(k.y, gx, j.y * fx), fmaf(k.z, gx, j.z * fx));
-      const float3 b75 = make_float3(fmaf(k.x, fx, j.x * gx), fmaf(k.y, fx, j.y * gx), fmaf(k.z, fx, j.z * gx));
-      unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
-      const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
-      uint2 oA, oB;
-      if (rowT) {
-        const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
-        const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
-        quad_pair<false>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
-        if (okA) *reinterpret_cast<uint2*>(orow) = oA;
-        if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
+    for (int q = 0; q < 2; q++) quad_cell(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+    __syncthreads();  // L, S and this tile buffer are free again
+  }
+}
+
+// ---- warp-specialised variant: one producer warp prepares tile i+1 (TMA wait, clamp fix-up, luma, terms) while
+// NWC consumer warps run phase 3 of tile i.  No CTA-wide barrier in the steady state: the hand-offs are mbarriers
+// (ready[b]: producer -> consumers, free_[b]: consumers -> producer), tile/L/S are all double-buffered.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NWC> struct __align__(128) QuadWsSmem {
+  uint2 tile[2][QuadCfg<NWC>::kPad];
+  float4 S[2][kQSW * QuadCfg<NWC>::kSH];
+  float L[2][QuadCfg<NWC>::kElems];
+  uint64_t tma[2], ready[2], free_[2];
+};
+
+template <int NWC, int MINB>
+__global__ void __launch_bounds__((NWC + 1) * 32, MINB)
+easu_h_quad2x_ws_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
+                        const int n_tiles, const int mbase) {
+  using C = QuadCfg<NWC>;
+  __shared__ QuadWsSmem<NWC> sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&sm.tma[b], 1);
+      mbar_init(&sm.ready[b], 1);
+      mbar_init(&sm.free_[b], NWC);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto box_x = [&](int t) { return (t % tiles_x) * kQCX - 2; };
+  auto box_y = [&](int t) { return mbase + (t / tiles_x) * C::kCY - 1; };
+  const int t0 = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = t0 < n_tiles ? (n_tiles - t0 + stride - 1) / stride : 0;
+
+  if (warp == NWC) {
+    // ------------------------------------------------------------------ producer warp
+    if (lane == 0 && my_tiles > 0) {
+      mbar_expect_tx(&sm.tma[0], C::kElems * 8u);
+      tma_load_2d(sm.tile[0], &tmap, box_x(t0), box_y(t0) - p.in.row0, &sm.tma[0]);
+    }
+    for (int it = 0; it < my_tiles; it++) {
+      const int b = it & 1, t = t0 + it * stride;
+      uint2* tile = sm.tile[b];
+      float* L = sm.L[b];
+      float4* S = sm.S[b];
+      const int gx0 = box_x(t), gy0 = box_y(t);
+      mbar_wait(&sm.tma[b], (it >> 1) & 1);
+      if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + C::kBH > p.in.h) {
+        for (int idx = lane; idx < C::kElems; idx += 32) {
+          const int j = idx / kQBW, i = idx - j * kQBW;
+          const int cy = clampi(gy0 + j, 0, p.in.h - 1) - gy0, cx = clampi(gx0 + i, 0, p.in.w - 1) - gx0;
+          if ((cx != i || cy != j) && cx >= 0 && cx < kQBW && cy >= 0 && cy < C::kBH) tile[idx] = tile[cy * kQBW + cx];
+        }
+        fence_proxy_async();
+        __syncwarp();
       }
-      if (rowB) {
-        const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
-        const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
-        quad_pair<true>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
-        if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
-        if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
+      for (int i = lane; i < C::kElems; i += 32) L[i] = texel_luma(tile[i]);
+      __syncwarp();
+      for (int idx = lane; idx < kQSW * C::kSH; idx += 32) {
+        const int j = idx / kQSW, i = idx - j * kQSW;
+        const float* c = L + (j + 1) * kQBW + (i + 1);
+        S[idx] = texel_terms(c[-kQBW], c[-1], c[0], c[1], c[kQBW]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.ready[b]);  // release: the warp's shared-memory writes are visible to waiters
+      // refill the OTHER buffer with tile it+1 once the consumers have finished tile it-1 (which used it)
+      if (it + 1 < my_tiles) {
+        if (it >= 1) mbar_wait(&sm.free_[b ^ 1], ((it - 1) >> 1) & 1);
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&sm.tma[b ^ 1], C::kElems * 8u);
+          tma_load_2d(sm.tile[b ^ 1], &tmap, box_x(t + stride), box_y(t + stride) - p.in.row0, &sm.tma[b ^ 1]);
+        }
+        __syncwarp();
       }
     }
-    __syncthreads();  // L, S and this tile buffer are free again
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    for (int it = 0; it < my_tiles; it++) {
+      const int b = it & 1, t = t0 + it * stride;
+      mbar_wait(&sm.ready[b], (it >> 1) & 1);
+      const int gx0 = box_x(t), gy0 = box_y(t);
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) quad_cell(p, sm.tile[b], sm.S[b], gx0, gy0, lane, warp + q * NWC);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.free_[b]);
+    }
   }
 }
 
@@ -463,6 +558,17 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
       *name = nm;
       return cudaGetLastError();
     };
+    if (variant == 3 || variant == 4) {  // warp-specialised: 4 consumer warps + 1 producer warp
+      constexpr int NWC = 4;
+      if (!make_tmap(&tmap, p.in, kQBW, QuadCfg<NWC>::kBH)) return cudaErrorNotSupported;
+      const int cy = QuadCfg<NWC>::kCY, tiles_y = (m_last - m_first + 1 + cy - 1) / cy, n_tiles = tiles_x * tiles_y;
+      const int per_sm = variant == 3 ? 5 : 4;
+      const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
+      if (variant == 3) easu_h_quad2x_ws_kernel<NWC, 5><<<grid, (NWC + 1) * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+      else easu_h_quad2x_ws_kernel<NWC, 4><<<grid, (NWC + 1) * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+      *name = variant == 3 ? "easu_h_quad2x_ws<4+1w,5/sm,tma2>" : "easu_h_quad2x_ws<4+1w,4/sm,tma2>";
+      return cudaGetLastError();
+    }
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");

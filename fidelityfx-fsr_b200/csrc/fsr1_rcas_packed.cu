@@ -20,8 +20,7 @@
 
 namespace fsr1 {
 
-constexpr int kRows = 4;    // rows walked by one lane
-constexpr int kWarps = 8;   // warps per CTA, stacked vertically: CTA = 60 x 32 output pixels
+constexpr int kWarps = 8;   // warps per CTA, stacked vertically: CTA = 60 x (8*kRows) output pixels (kRows = rows walked by one lane)
 constexpr int kSpan = 60;   // output pixels per warp per row (lanes 1..30)
 
 struct Row3 { __half2 r, g, b; };  // (pixel0, pixel1) per channel
@@ -89,7 +88,7 @@ __device__ __forceinline__ __half2 resolve_channel(__half2 lobe, __half2 rcpL, _
   return __hmul2(__hfma2(lobe, ring, e), rcpL);
 }
 
-template <bool kChecked, bool kClamp, bool kNewton>
+template <bool kChecked, bool kClamp, bool kNewton, int kRows>
 __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, int lane) {
   const __half2 sharp = uh2(p.sharp_h2);
   const __half2 kLimit = __float2half2_rn(-0.1875f), kZero = __float2half2_rn(0.0f);
@@ -97,8 +96,15 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
   const bool writer = lane >= 1 && lane <= 30 && (!kChecked || x < p.out.w);
   // all kRows+2 rows are requested up front: kRows+2 independent 16-byte loads in flight per lane
   Row3 rows[kRows + 2];
+  if (!kChecked) {  // one 64-bit address, then += pitch: no per-row address arithmetic
+    const unsigned char* src = p.in.base + (long long)(ys - 1 - p.in.row0) * p.in.pitch + (long long)x * 8;
 #pragma unroll
-  for (int r = 0; r < kRows + 2; r++) rows[r] = load_pair<kChecked, kClamp>(p, x, ys - 1 + r);
+    for (int r = 0; r < kRows + 2; r++) rows[r] = to_soa(__ldg(reinterpret_cast<const uint4*>(src + (long long)r * p.in.pitch)));
+  } else {
+#pragma unroll
+    for (int r = 0; r < kRows + 2; r++) rows[r] = load_pair<kChecked, kClamp>(p, x, ys - 1 + r);
+  }
+  unsigned char* dst = p.out.base + (long long)(ys - p.out.row0) * p.out.pitch + (long long)x * 8;
 #pragma unroll
   for (int r = 0; r < kRows; r++) {
     const int y = ys + r;
@@ -125,7 +131,7 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
     const __half2 oB = resolve_channel(lobe, rcpL, prev.b, dB, cur.b, fB, next.b);
 
     if (writer) {
-      unsigned char* o = p.out.base + (long long)(y - p.out.row0) * p.out.pitch + (long long)x * 8;
+      unsigned char* o = dst + (long long)r * p.out.pitch;
       const uint32_t rg0 = __byte_perm(hu2(oR), hu2(oG), 0x5410), b0 = __byte_perm(hu2(oB), one, 0x5410);
       if (!kChecked || x + 1 < p.out.w) {
         const uint32_t rg1 = __byte_perm(hu2(oR), hu2(oG), 0x7632), b1 = __byte_perm(hu2(oB), one, 0x7632);
@@ -137,7 +143,7 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
   }
 }
 
-template <bool kClamp, bool kNewton>
+template <bool kClamp, bool kNewton, int kRows>
 __global__ void __launch_bounds__(32 * kWarps) rcas_h_packed_kernel(const RcasParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kSpan - 2;  // even -> every lane's pair is 16-byte aligned
@@ -146,25 +152,30 @@ __global__ void __launch_bounds__(32 * kWarps) rcas_h_packed_kernel(const RcasPa
   if (ys >= p.y1) return;  // whole warp
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kRows < p.in.h && ys + kRows <= p.y1;
   if (interior)
-    rcas_rows<false, kClamp, kNewton>(p, x, ys, lane);
+    rcas_rows<false, kClamp, kNewton, kRows>(p, x, ys, lane);
   else
-    rcas_rows<true, kClamp, kNewton>(p, x, ys, lane);
+    rcas_rows<true, kClamp, kNewton, kRows>(p, x, ys, lane);
 }
 
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name) {
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
-  const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + kWarps * kRows - 1) / (kWarps * kRows), 1);
-  static int variant = -1;  // development knob: FSR1_RCAS_VARIANT = 0 (MUFU reciprocals), 1 (Newton on the fp16 pipe)
+  static int variant = -1;  // development knob: FSR1_RCAS_VARIANT = 0 (4 rows/lane, MUFU), 1 (4 rows, Newton), 2 (8 rows/lane, MUFU)
   if (variant < 0) { const char* e = getenv("FSR1_RCAS_VARIANT"); variant = e ? atoi(e) : 0; }
+  const int rows_per_cta = kWarps * (variant == 2 ? 8 : 4);
+  const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + rows_per_cta - 1) / rows_per_cta, 1);
   if (variant == 1) {
-    if (p.clamp) rcas_h_packed_kernel<true, true><<<grid, 32 * kWarps, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, true><<<grid, 32 * kWarps, 0, s>>>(p);
+    if (p.clamp) rcas_h_packed_kernel<true, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
     *name = "rcas_h_packed<2px,4rows,shfl60,newton>";
+  } else if (variant == 2) {
+    if (p.clamp) rcas_h_packed_kernel<true, false, 8><<<grid, 32 * kWarps, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, false, 8><<<grid, 32 * kWarps, 0, s>>>(p);
+    *name = "rcas_h_packed<2px,8rows,shfl60,mufu>";
   } else {
-    if (p.clamp) rcas_h_packed_kernel<true, false><<<grid, 32 * kWarps, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, false><<<grid, 32 * kWarps, 0, s>>>(p);
+    if (p.clamp) rcas_h_packed_kernel<true, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
     *name = "rcas_h_packed<2px,4rows,shfl60,mufu>";
   }
   return cudaGetLastError();
