@@ -189,6 +189,9 @@ def time_cpu(wl, steps, warmup, budget_s):
 
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
+    global RING
+    if args.frames > 0:
+        RING = args.frames
     import numpy as np
     import torch
     import fsr1_b200 as F
@@ -213,7 +216,12 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     out = {}
     if world == 1:
-        ins = [torch.from_numpy(host_frame(12345 + t)).to(dev) for t in range(RING)]
+        def resident(a):  # rows padded to a 16-byte multiple, like any texture allocation (TMA / 128-bit access need it)
+            h, w = a.shape[:2]
+            buf = torch.zeros((h, (w + 1) & ~1, 4), dtype=tdt, device=dev)
+            buf[:, :w] = torch.from_numpy(a).to(dev)
+            return buf[:, :w]
+        ins = [resident(host_frame(12345 + t)) for t in range(RING)]
         tmps = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
         outs = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
         imgs = [(api.image(ins[i]), api.image(tmps[i]), api.image(outs[i])) for i in range(RING)]
@@ -416,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-4k-fp16", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")
