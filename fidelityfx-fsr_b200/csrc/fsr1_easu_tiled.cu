@@ -68,6 +68,106 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
 // =======================================================================================================
 constexpr int kTileW = 64, kTileH = 16;
 
+// One vertical pixel pair of the generic kernel: pixel A (row oy) and B (row oy+1) in the same output column.
+// t0/q0 point at tap (0,0) / texel f of pixel A; DR = fy(B) - fy(A) in {0,1}.  Packed lanes are (A, B).
+template <int DR>
+__device__ __forceinline__ void vpair(const uint2* __restrict__ t0, const float4* __restrict__ q0, int BW, int SW, float ppx,
+                                      float ppyA, float ppyB, uint2& outA, uint2& outB) {
+  // fp32: blend of the f,g,j,k terms (reference order) and the filter shape, per pixel
+  const float4 f = q0[0], g = q0[1], j = q0[SW], k = q0[SW + 1];
+  const float ipx = 1.0f - ppx;
+  Shape sA, sB;
+  {
+    const float ipy = 1.0f - ppyA, wf = ipx * ipy, wg = ppx * ipy, wj = ipx * ppyA, wk = ppx * ppyA;
+    sA = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))), fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
+                     fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
+  }
+  {
+    const float4 f2 = DR ? j : f, g2 = DR ? k : g, j2 = DR ? q0[2 * SW] : j, k2 = DR ? q0[2 * SW + 1] : k;
+    const float ipy = 1.0f - ppyB, wf = ipx * ipy, wg = ppx * ipy, wj = ipx * ppyB, wk = ppx * ppyB;
+    sB = pixel_shape(fmaf(k2.x, wk, fmaf(j2.x, wj, fmaf(g2.x, wg, f2.x * wf))), fmaf(k2.y, wk, fmaf(j2.y, wj, fmaf(g2.y, wg, f2.y * wf))),
+                     fmaf(k2.z, wk, fmaf(j2.z, wj, fmaf(g2.z, wg, f2.z * wf))));
+  }
+  const __half2 qa = __floats2half2_rn(sA.qa, sB.qa), qb = __floats2half2_rn(sA.qb, sB.qb);
+  const __half2 qc = __floats2half2_rn(sA.qc, sB.qc), lob = __floats2half2_rn(sA.lob, sB.lob);
+  const __half2 clp = __floats2half2_rn(sA.clp, sB.clp);
+  // d2(k,r) = PX[k] + QY[r] + SB[k]*OY[r]; the column offset is the same for both pixels, the row offset is not
+  const __half2 ppy2 = __floats2half2_rn(ppyA, ppyB), ppx2 = __float2half2_rn(ppx);
+  __half2 PX[4], SB[4], QY[4], OY[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const __half2 oxk = __hsub2(h2c((float)(i - 1)), ppx2);
+    SB[i] = __hmul2(qb, oxk);
+    PX[i] = __hmul2(__hmul2(qa, oxk), oxk);
+    OY[i] = __hsub2(h2c((float)(i - 1)), ppy2);
+    QY[i] = __hmul2(__hmul2(qc, OY[i]), OY[i]);
+  }
+  const __half2 kZero = h2c(0.0f), one = h2c(1.0f);
+  if (DR == 0) {
+    // same window for both pixels: colour accumulators in structure-of-arrays form (A,B) per channel
+    __half2 aR = kZero, aG = kZero, aB = kZero, aW = kZero;
+#define FSR1_VTAP0(R, K)                                                                     \
+    {                                                                                        \
+      const uint2 c = t0[(R) * BW + (K)];                                                    \
+      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);  \
+      aR = __hfma2(__low2half2(u2h2(c.x)), w, aR);                                           \
+      aG = __hfma2(__high2half2(u2h2(c.x)), w, aG);                                          \
+      aB = __hfma2(__low2half2(u2h2(c.y)), w, aB);                                           \
+      aW = __hadd2(aW, w);                                                                   \
+    }
+    FSR1_VTAP0(0, 1) FSR1_VTAP0(0, 2) FSR1_VTAP0(1, 0) FSR1_VTAP0(1, 3)   // far taps first (see quad_pair)
+    FSR1_VTAP0(2, 0) FSR1_VTAP0(2, 3) FSR1_VTAP0(3, 1) FSR1_VTAP0(3, 2)
+    FSR1_VTAP0(1, 1) FSR1_VTAP0(1, 2) FSR1_VTAP0(2, 1) FSR1_VTAP0(2, 2)
+#undef FSR1_VTAP0
+    const uint2 cf = t0[BW + 1], cg = t0[BW + 2], cj = t0[2 * BW + 1], ck = t0[2 * BW + 2];
+    const __half2 mnRG = __hmin2(__hmin2(u2h2(cf.x), u2h2(cg.x)), __hmin2(u2h2(cj.x), u2h2(ck.x)));
+    const __half2 mxRG = __hmax2(__hmax2(u2h2(cf.x), u2h2(cg.x)), __hmax2(u2h2(cj.x), u2h2(ck.x)));
+    const __half2 mnBA = __hmin2(__hmin2(u2h2(cf.y), u2h2(cg.y)), __hmin2(u2h2(cj.y), u2h2(ck.y)));
+    const __half2 mxBA = __hmax2(__hmax2(u2h2(cf.y), u2h2(cg.y)), __hmax2(u2h2(cj.y), u2h2(ck.y)));
+    const float2 aWf = __half22float2(aW);
+    const __half2 r = __floats2half2_rn(rcp_approx(aWf.x), rcp_approx(aWf.y));
+    const __half2 oR = __hmin2(__low2half2(mxRG), __hmax2(__low2half2(mnRG), __hmul2(aR, r)));
+    const __half2 oG = __hmin2(__high2half2(mxRG), __hmax2(__high2half2(mnRG), __hmul2(aG, r)));
+    const __half2 oB = __hmin2(__low2half2(mxBA), __hmax2(__low2half2(mnBA), __hmul2(aB, r)));
+    outA = make_uint2(h22u(__lows2half2(oR, oG)), h22u(__lows2half2(oB, one)));
+    outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
+  } else {
+    // pixel B's window is one input row further down: tap (R,K) of A is texel row R, of B texel row R+1
+    __half2 aRG_A = kZero, aBA_A = kZero, aRG_B = kZero, aBA_B = kZero, aW = kZero;
+#define FSR1_VTAP1(R, K)                                                                     \
+    {                                                                                        \
+      const uint2 ca = t0[(R) * BW + (K)], cb = t0[((R) + 1) * BW + (K)];                    \
+      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);  \
+      const __half2 wA2 = __low2half2(w), wB2 = __high2half2(w);                             \
+      aRG_A = __hfma2(u2h2(ca.x), wA2, aRG_A);                                               \
+      aBA_A = __hfma2(u2h2(ca.y), wA2, aBA_A);                                               \
+      aRG_B = __hfma2(u2h2(cb.x), wB2, aRG_B);                                               \
+      aBA_B = __hfma2(u2h2(cb.y), wB2, aBA_B);                                               \
+      aW = __hadd2(aW, w);                                                                   \
+    }
+    FSR1_VTAP1(0, 1) FSR1_VTAP1(0, 2) FSR1_VTAP1(1, 0) FSR1_VTAP1(1, 3)
+    FSR1_VTAP1(2, 0) FSR1_VTAP1(2, 3) FSR1_VTAP1(3, 1) FSR1_VTAP1(3, 2)
+    FSR1_VTAP1(1, 1) FSR1_VTAP1(1, 2) FSR1_VTAP1(2, 1) FSR1_VTAP1(2, 2)
+#undef FSR1_VTAP1
+    const uint2 r1a = t0[BW + 1], r1b = t0[BW + 2], r2a = t0[2 * BW + 1], r2b = t0[2 * BW + 2];
+    const uint2 r3a = t0[3 * BW + 1], r3b = t0[3 * BW + 2];
+    const __half2 midMnRG = __hmin2(u2h2(r2a.x), u2h2(r2b.x)), midMxRG = __hmax2(u2h2(r2a.x), u2h2(r2b.x));
+    const __half2 midMnBA = __hmin2(u2h2(r2a.y), u2h2(r2b.y)), midMxBA = __hmax2(u2h2(r2a.y), u2h2(r2b.y));
+    const __half2 mnRG_A = __hmin2(__hmin2(u2h2(r1a.x), u2h2(r1b.x)), midMnRG), mxRG_A = __hmax2(__hmax2(u2h2(r1a.x), u2h2(r1b.x)), midMxRG);
+    const __half2 mnBA_A = __hmin2(__hmin2(u2h2(r1a.y), u2h2(r1b.y)), midMnBA), mxBA_A = __hmax2(__hmax2(u2h2(r1a.y), u2h2(r1b.y)), midMxBA);
+    const __half2 mnRG_B = __hmin2(__hmin2(u2h2(r3a.x), u2h2(r3b.x)), midMnRG), mxRG_B = __hmax2(__hmax2(u2h2(r3a.x), u2h2(r3b.x)), midMxRG);
+    const __half2 mnBA_B = __hmin2(__hmin2(u2h2(r3a.y), u2h2(r3b.y)), midMnBA), mxBA_B = __hmax2(__hmax2(u2h2(r3a.y), u2h2(r3b.y)), midMxBA);
+    const float2 aWf = __half22float2(aW);
+    const __half2 rA = __float2half2_rn(rcp_approx(aWf.x)), rB = __float2half2_rn(rcp_approx(aWf.y));
+    const __half2 oRG_A = __hmin2(mxRG_A, __hmax2(mnRG_A, __hmul2(aRG_A, rA)));
+    const __half2 oBA_A = __hmin2(mxBA_A, __hmax2(mnBA_A, __hmul2(aBA_A, rA)));
+    const __half2 oRG_B = __hmin2(mxRG_B, __hmax2(mnRG_B, __hmul2(aRG_B, rB)));
+    const __half2 oBA_B = __hmin2(mxBA_B, __hmax2(mnBA_B, __hmul2(aBA_B, rB)));
+    outA = make_uint2(h22u(oRG_A), h22u(__lows2half2(oBA_A, one)));   // alpha = 1 (FSR_Pass.hlsl:95)
+    outB = make_uint2(h22u(oRG_B), h22u(__lows2half2(oBA_B, one)));
+  }
+}
+
 // dynamic shared memory: [tile0][tile1][luma][terms][2 mbarriers], every part 128-byte aligned
 __host__ __device__ inline size_t pairs_tile_stride(int BW, int BH) { return ((size_t)BW * BH * 8 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
@@ -151,99 +251,33 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
   }
   __syncthreads();
 
-  // phase 3
+  // phase 3: a lane owns one output column and the VERTICAL pixel pair (oy, oy+1).  Whether the two rows fall in
+  // the same input cell row (DR = 0) or in consecutive ones (DR = 1) depends on oy only, so it is warp-uniform:
+  // DR = 0 loads 12 taps + 4 term vectors once for both pixels, DR = 1 loads a 5-row window (16 + 6).  Lanes walk
+  // the input row at < 1 texel per lane: shared-memory reads are (nearly) conflict-free, which the earlier
+  // horizontal pairing (1.3-2 texels per lane, two windows per lane) was not — it was LSU-bound (ncu: 72 %).
 #pragma unroll 1
-  for (int pr = 0; pr < kTileH / 8; pr++) {
-    const int ox = ox0 + lane * 2, oy = oy0 + warp + pr * 8;
-    if (ox >= p.out.w || oy >= p.y1) continue;
-    int fxA, fxB, fy;
-    float ppxA, ppxB, ppy;
-    easu_pos(ox, p.c0x, p.c0z, fxA, ppxA);
-    easu_pos(ox + 1 < p.out.w ? ox + 1 : ox, p.c0x, p.c0z, fxB, ppxB);  // odd width: B duplicates A
-    easu_pos(oy, p.c0y, p.c0w, fy, ppy);
-    const int cy = fy - fy0, cxA = fxA - fx0, cxB = fxB - fx0;  // >= 1 by construction
-
-    // fp32: blend of the f,g,j,k terms and the filter shape, per pixel
-    Shape sA, sB;
-    {
-      const float ipy = 1.0f - ppy;
-      const float4* q = S + (cy - 1) * SW + (cxA - 1);
-      float4 f = q[0], g = q[1], j = q[SW], k = q[SW + 1];
-      float ipx = 1.0f - ppxA, wf = ipx * ipy, wg = ppxA * ipy, wj = ipx * ppy, wk = ppxA * ppy;
-      sA = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))),
-                       fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
-                       fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
-      q = S + (cy - 1) * SW + (cxB - 1);
-      f = q[0]; g = q[1]; j = q[SW]; k = q[SW + 1];
-      ipx = 1.0f - ppxB; wf = ipx * ipy; wg = ppxB * ipy; wj = ipx * ppy; wk = ppxB * ppy;
-      sB = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))),
-                       fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
-                       fmaf(k.z, wk, fmaf(j.z, wj, fmaf(g.z, wg, f.z * wf))));
-    }
-    const __half2 qa = __floats2half2_rn(sA.qa, sB.qa), qb = __floats2half2_rn(sA.qb, sB.qb);
-    const __half2 qc = __floats2half2_rn(sA.qc, sB.qc), lob = __floats2half2_rn(sA.lob, sB.lob);
-    const __half2 clp = __floats2half2_rn(sA.clp, sB.clp);
-
-    // per-column / per-row pieces of d2:  d2(k,r) = PX[k] + QY[r] + SB[k]*OY[r]
-    const __half2 ppx2 = __floats2half2_rn(ppxA, ppxB), ppy2 = __float2half2_rn(ppy);
-    __half2 PX[4], SB[4], QY[4], OY[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const __half2 oxk = __hsub2(h2c((float)(k - 1)), ppx2);
-      SB[k] = __hmul2(qb, oxk);
-      PX[k] = __hmul2(__hmul2(qa, oxk), oxk);
-      OY[k] = __hsub2(h2c((float)(k - 1)), ppy2);
-      QY[k] = __hmul2(__hmul2(qc, OY[k]), OY[k]);
-    }
-
-    const uint2* tA0 = tile + (cy - 1) * BW + (cxA - 1);
-    const uint2* tB0 = tile + (cy - 1) * BW + (cxB - 1);
-    const __half2 kZero = h2c(0.0f);
-    __half2 aRG_A = kZero, aBA_A = kZero, aRG_B = kZero, aBA_B = kZero, aW = kZero;
-    __half2 mnRG_A, mnBA_A, mxRG_A, mxBA_A, mnRG_B, mnBA_B, mxRG_B, mxBA_B;
-
-#define FSR1_TAP(R, K)                                                                             \
-    {                                                                                              \
-      const uint2 ca = tA0[(R) * BW + (K)], cb = tB0[(R) * BW + (K)];                              \
-      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);        \
-      const __half2 wA2 = __low2half2(w), wB2 = __high2half2(w);                                   \
-      aRG_A = __hfma2(u2h2(ca.x), wA2, aRG_A);                                                     \
-      aBA_A = __hfma2(u2h2(ca.y), wA2, aBA_A);                                                     \
-      aRG_B = __hfma2(u2h2(cb.x), wB2, aRG_B);                                                     \
-      aBA_B = __hfma2(u2h2(cb.y), wB2, aBA_B);                                                     \
-      aW = __hadd2(aW, w);                                                                         \
-      if ((R) == 1 && (K) == 1) {                                                                  \
-        mnRG_A = mxRG_A = u2h2(ca.x); mnBA_A = mxBA_A = u2h2(ca.y);                                \
-        mnRG_B = mxRG_B = u2h2(cb.x); mnBA_B = mxBA_B = u2h2(cb.y);                                \
-      } else if (((R) == 1 || (R) == 2) && ((K) == 1 || (K) == 2)) {                               \
-        mnRG_A = __hmin2(mnRG_A, u2h2(ca.x)); mxRG_A = __hmax2(mxRG_A, u2h2(ca.x));                \
-        mnBA_A = __hmin2(mnBA_A, u2h2(ca.y)); mxBA_A = __hmax2(mxBA_A, u2h2(ca.y));                \
-        mnRG_B = __hmin2(mnRG_B, u2h2(cb.x)); mxRG_B = __hmax2(mxRG_B, u2h2(cb.x));                \
-        mnBA_B = __hmin2(mnBA_B, u2h2(cb.y)); mxBA_B = __hmax2(mxBA_B, u2h2(cb.y));                \
-      }                                                                                            \
-    }
-    // far taps first, the four near taps (largest weights) last: the half accumulators then round at small
-    // magnitude for 8 of the 12 steps — measured 45 % less error than near-first at no cost
-    FSR1_TAP(0, 1) FSR1_TAP(0, 2)                                 // b c
-    FSR1_TAP(1, 0) FSR1_TAP(1, 3)                                 // e h
-    FSR1_TAP(2, 0) FSR1_TAP(2, 3)                                 // i l
-    FSR1_TAP(3, 1) FSR1_TAP(3, 2)                                 // n o
-    FSR1_TAP(1, 1) FSR1_TAP(1, 2) FSR1_TAP(2, 1) FSR1_TAP(2, 2)   // f g j k
-#undef FSR1_TAP
-
-    const float2 aWf = __half22float2(aW);
-    const __half2 rA = __float2half2_rn(rcp_approx(aWf.x)), rB = __float2half2_rn(rcp_approx(aWf.y));
-    __half2 oRG_A = __hmin2(mxRG_A, __hmax2(mnRG_A, __hmul2(aRG_A, rA)));
-    __half2 oBA_A = __hmin2(mxBA_A, __hmax2(mnBA_A, __hmul2(aBA_A, rA)));
-    __half2 oRG_B = __hmin2(mxRG_B, __hmax2(mnRG_B, __hmul2(aRG_B, rB)));
-    __half2 oBA_B = __hmin2(mxBA_B, __hmax2(mnBA_B, __hmul2(aBA_B, rB)));
-    oBA_A = __halves2half2(__low2half(oBA_A), __float2half_rn(1.0f));  // alpha = 1 (FSR_Pass.hlsl:95)
-    oBA_B = __halves2half2(__low2half(oBA_B), __float2half_rn(1.0f));
-    unsigned char* orow = p.out.base + (long long)(oy - p.out.row0) * p.out.pitch;
-    if (ox + 1 < p.out.w) {
-      *reinterpret_cast<uint4*>(orow + (size_t)ox * 8) = make_uint4(h22u(oRG_A), h22u(oBA_A), h22u(oRG_B), h22u(oBA_B));
-    } else {
-      *reinterpret_cast<uint2*>(orow + (size_t)ox * 8) = make_uint2(h22u(oRG_A), h22u(oBA_A));
+  for (int job = warp; job < (kTileW / 32) * (kTileH / 2); job += kThreads / 32) {
+    const int oyA = oy0 + (job >> 1) * 2;
+    if (oyA >= p.y1) continue;  // warp-uniform
+    const bool hasB = oyA + 1 < p.y1;
+    const int oxr = ox0 + (job & 1) * 32 + lane;
+    const bool active = oxr < p.out.w;
+    const int ox = active ? oxr : p.out.w - 1;
+    int fx, fyA, fyB;
+    float ppx, ppyA, ppyB;
+    easu_pos(ox, p.c0x, p.c0z, fx, ppx);
+    easu_pos(oyA, p.c0y, p.c0w, fyA, ppyA);
+    easu_pos(hasB ? oyA + 1 : oyA, p.c0y, p.c0w, fyB, ppyB);
+    const uint2* t0 = tile + (fyA - fy0 - 1) * BW + (fx - fx0 - 1);       // window origin: tap (0,0) of pixel A
+    const float4* q0 = S + (fyA - fy0 - 1) * SW + (fx - fx0 - 1);          // term vector of texel f of pixel A
+    uint2 oA, oB;
+    if (fyB == fyA) vpair<0>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
+    else vpair<1>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
+    if (active) {
+      unsigned char* o = p.out.base + (long long)(oyA - p.out.row0) * p.out.pitch + (long long)ox * 8;
+      *reinterpret_cast<uint2*>(o) = oA;
+      if (hasB) *reinterpret_cast<uint2*>(o + p.out.pitch) = oB;
     }
   }
   __syncthreads();  // L, S and this tile buffer are free again
@@ -574,6 +608,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     return launch(easu_h_quad2x_kernel<4, 6>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");
   }
 
+  if (!(p.c0x > 0.0f && p.c0x <= 1.0f && p.c0y > 0.0f && p.c0y <= 1.0f)) return cudaErrorNotSupported;  // upscaling only
   int BW = max_footprint(p.out.w, 0, kTileW, p.c0x, p.c0z, true);
   int BH = max_footprint(p.y1, p.y0, kTileH, p.c0y, p.c0w, false);
   BW = (BW + 1) & ~1;  // inner box extent must be a multiple of 16 bytes
@@ -592,7 +627,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 220 * 1024) per_sm--;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
   easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
-  *name = "easu_h_pairs<64x16,persistent,tma2>";
+  *name = "easu_h_vpairs<64x16,persistent,tma2>";
   return cudaGetLastError();
 }
 
