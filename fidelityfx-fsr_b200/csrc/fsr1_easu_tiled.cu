@@ -66,7 +66,7 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
 // =======================================================================================================
 //  generic kernel: any scale, lane = pixel pair (2*lane, 2*lane+1), rows warp and warp+8 of a 64x16 tile
 // =======================================================================================================
-constexpr int kTileW = 64, kTileH = 16;
+constexpr int kTileW = 64, kTileH = 32;
 
 // One vertical pixel pair of the generic kernel: pixel A (row oy) and B (row oy+1) in the same output column.
 // t0/q0 point at tap (0,0) / texel f of pixel A; DR = fy(B) - fy(A) in {0,1}.  Packed lanes are (A, B).
@@ -627,7 +627,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 220 * 1024) per_sm--;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
   easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
-  *name = "easu_h_vpairs<64x16,persistent,tma2>";
+  *name = "easu_h_vpairs<64x32,persistent,tma2>";
   return cudaGetLastError();
 }
 
