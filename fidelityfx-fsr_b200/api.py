@@ -8,6 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
+from ._lib import FORMAT_RGB10A2_UNORM, FORMAT_RGBA8_UNORM  # noqa: F401
 from ._lib import (FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_H_REFERENCE, FLAG_NO_RCAS, FLAG_PRECISE, FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_RCAS_CLAMP, FORMAT_RGBA16F,  # noqa: F401
                    FORMAT_RGBA32F, Fsr1Error, Image)
 
@@ -51,11 +52,14 @@ def image(t, height=None, row0=0):
     """Describe tensor `t` ([rows, W, 4]) as logical rows [row0, row0+rows) of an image `height` rows tall."""
     if not t.is_cuda:
         raise Fsr1Error("fsr1 kernels run on CUDA tensors only (no CPU path)")
-    if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
-        raise Fsr1Error("image tensors must be [rows, width, 4] with contiguous pixels")
-    fmt = {torch.float16: FORMAT_RGBA16F, torch.float32: FORMAT_RGBA32F}.get(t.dtype)
-    if fmt is None:
-        raise Fsr1Error("unsupported dtype %s" % t.dtype)
+    if t.dim() == 2 and t.dtype == torch.int32 and t.stride(1) == 1:      # R10G10B10A2_UNORM: one int32 per pixel
+        fmt = FORMAT_RGB10A2_UNORM
+    else:
+        if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
+            raise Fsr1Error("image tensors must be [rows, width, 4] with contiguous pixels (or [rows, width] int32 for RGB10A2)")
+        fmt = {torch.float16: FORMAT_RGBA16F, torch.float32: FORMAT_RGBA32F, torch.uint8: FORMAT_RGBA8_UNORM}.get(t.dtype)
+        if fmt is None:
+            raise Fsr1Error("unsupported dtype %s" % t.dtype)
     rows, w = int(t.shape[0]), int(t.shape[1])
     return Image(t.data_ptr(), t.stride(0) * t.element_size(), w, int(height if height is not None else rows), row0,
                  rows, fmt, 0)

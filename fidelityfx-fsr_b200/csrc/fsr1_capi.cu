@@ -22,15 +22,22 @@ int cuda_fail(cudaError_t e) {
   return FSR1_ERR_CUDA;
 }
 
-int bytes_per_pixel(uint32_t fmt) { return fmt == FSR1_FORMAT_RGBA16F ? 8 : (fmt == FSR1_FORMAT_RGBA32F ? 16 : 0); }
+int bytes_per_pixel(uint32_t fmt) {
+  switch (fmt) {
+    case FSR1_FORMAT_RGBA16F: return 8;
+    case FSR1_FORMAT_RGBA32F: return 16;
+    case FSR1_FORMAT_RGBA8_UNORM: case FSR1_FORMAT_RGB10A2_UNORM: return 4;
+    default: return 0;
+  }
+}
 
 int check_image(const fsr1_image* im) {
   if (!im || !im->data || im->width == 0 || im->height == 0 || im->rows == 0) return FSR1_ERR_INVALID_ARGUMENT;
   const int bpp = bytes_per_pixel(im->format);
   if (!bpp) return FSR1_ERR_INVALID_ARGUMENT;
   if (im->width > 32768u || im->height > 32768u) return FSR1_ERR_INVALID_ARGUMENT;
-  if (im->pitch_bytes < (uint64_t)im->width * bpp || (im->pitch_bytes % (bpp == 8 ? 8 : 16)) != 0) return FSR1_ERR_INVALID_ARGUMENT;
-  if ((uintptr_t)im->data % (bpp == 8 ? 8 : 16) != 0) return FSR1_ERR_INVALID_ARGUMENT;
+  if (im->pitch_bytes < (uint64_t)im->width * bpp || (im->pitch_bytes % bpp) != 0) return FSR1_ERR_INVALID_ARGUMENT;
+  if ((uintptr_t)im->data % bpp != 0) return FSR1_ERR_INVALID_ARGUMENT;
   if ((uint64_t)im->row0 + im->rows > im->height) return FSR1_ERR_INVALID_ARGUMENT;
   return FSR1_OK;
 }

@@ -100,6 +100,47 @@ template <> struct Px<__half> {
   }
 };
 
+// UNORM storage (the formats the sample actually renders into: R8G8B8A8_UNORM, R10G10B10A2_UNORM,
+// sample/src/DX12/FSR_Filter.cpp:72-73).  Conversions follow the D3D rules: unorm -> float is c / (2^n - 1),
+// float -> unorm is clamp to [0,1] (NaN -> 0), scale by 2^n - 1, add 0.5, truncate.  4 bytes per pixel.
+struct Unorm8 {};
+struct Unorm10 {};
+__device__ __forceinline__ uint32_t to_unorm(float v, float scale) {
+  return (uint32_t)__fadd_rn(__fmul_rn(__saturatef(v), scale), 0.5f);
+}
+template <> struct Px<Unorm8> {
+  static constexpr int kBytes = 4;
+  static __device__ __forceinline__ float3 load(const ImgView& im, int x, int y) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return make_float3(__fdiv_rn((float)(v & 255u), 255.0f), __fdiv_rn((float)((v >> 8) & 255u), 255.0f),
+                       __fdiv_rn((float)((v >> 16) & 255u), 255.0f));
+  }
+  static __device__ __forceinline__ float alpha(const ImgView& im, int x, int y) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return __fdiv_rn((float)(v >> 24), 255.0f);
+  }
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b, float a = 1.0f) {
+    reinterpret_cast<uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch)[x] =
+        to_unorm(r, 255.0f) | (to_unorm(g, 255.0f) << 8) | (to_unorm(b, 255.0f) << 16) | (to_unorm(a, 255.0f) << 24);
+  }
+};
+template <> struct Px<Unorm10> {
+  static constexpr int kBytes = 4;
+  static __device__ __forceinline__ float3 load(const ImgView& im, int x, int y) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return make_float3(__fdiv_rn((float)(v & 1023u), 1023.0f), __fdiv_rn((float)((v >> 10) & 1023u), 1023.0f),
+                       __fdiv_rn((float)((v >> 20) & 1023u), 1023.0f));
+  }
+  static __device__ __forceinline__ float alpha(const ImgView& im, int x, int y) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch) + x);
+    return __fdiv_rn((float)(v >> 30), 3.0f);
+  }
+  static __device__ __forceinline__ void store(const ImgView& im, int x, int y, float r, float g, float b, float a = 1.0f) {
+    reinterpret_cast<uint32_t*>(im.base + (long long)(y - im.row0) * im.pitch)[x] =
+        to_unorm(r, 1023.0f) | (to_unorm(g, 1023.0f) << 10) | (to_unorm(b, 1023.0f) << 20) | (to_unorm(a, 3.0f) << 30);
+  }
+};
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // launchers (defined in the .cu files, called from fsr1_capi.cu)

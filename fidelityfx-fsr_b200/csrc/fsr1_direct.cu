@@ -199,27 +199,48 @@ __global__ void __launch_bounds__(256) rcas_direct_kernel(const RcasParams p) {
 
 static inline dim3 grid_for(int w, int rows) { return dim3((w + 31) / 32, (rows + 7) / 8, 1); }
 
+template <typename S>
+static void launch_easu_s(const EasuParams& p, bool exact, cudaStream_t s, dim3 grid, dim3 block) {
+  if (exact) easu_direct_kernel<S, true><<<grid, block, 0, s>>>(p);
+  else easu_direct_kernel<S, false><<<grid, block, 0, s>>>(p);
+}
+template <typename S>
+static void launch_rcas_s(const RcasParams& p, bool exact, cudaStream_t s, dim3 grid, dim3 block) {
+  if (exact) rcas_direct_kernel<S, true><<<grid, block, 0, s>>>(p);
+  else rcas_direct_kernel<S, false><<<grid, block, 0, s>>>(p);
+}
+static const char* direct_name(const char* pass, int format, bool exact) {
+  static const char* names[2][4][2] = {
+      {{"easu_direct<f16io,fast>", "easu_direct<f16io,exact>"}, {"easu_direct<f32,fast>", "easu_direct<f32,exact>"},
+       {"easu_direct<unorm8,fast>", "easu_direct<unorm8,exact>"}, {"easu_direct<unorm10,fast>", "easu_direct<unorm10,exact>"}},
+      {{"rcas_direct<f16io,fast>", "rcas_direct<f16io,exact>"}, {"rcas_direct<f32,fast>", "rcas_direct<f32,exact>"},
+       {"rcas_direct<unorm8,fast>", "rcas_direct<unorm8,exact>"}, {"rcas_direct<unorm10,fast>", "rcas_direct<unorm10,exact>"}}};
+  return names[pass[0] == 'r'][format - 1][exact ? 1 : 0];
+}
+
 cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name) {
   const dim3 block(32, 8, 1), grid = grid_for(p.out.w, p.y1 - p.y0);
-  if (format == 2) {
-    if (exact) { easu_direct_kernel<float, true><<<grid, block, 0, s>>>(p); *name = "easu_direct<f32,exact>"; }
-    else       { easu_direct_kernel<float, false><<<grid, block, 0, s>>>(p); *name = "easu_direct<f32,fast>"; }
-  } else {
-    if (exact) { easu_direct_kernel<__half, true><<<grid, block, 0, s>>>(p); *name = "easu_direct<f16io,exact>"; }
-    else       { easu_direct_kernel<__half, false><<<grid, block, 0, s>>>(p); *name = "easu_direct<f16io,fast>"; }
+  switch (format) {
+    case 1: launch_easu_s<__half>(p, exact, s, grid, block); break;
+    case 2: launch_easu_s<float>(p, exact, s, grid, block); break;
+    case 3: launch_easu_s<Unorm8>(p, exact, s, grid, block); break;
+    case 4: launch_easu_s<Unorm10>(p, exact, s, grid, block); break;
+    default: return cudaErrorInvalidValue;
   }
+  *name = direct_name("easu", format, exact);
   return cudaGetLastError();
 }
 
 cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cudaStream_t s, const char** name) {
   const dim3 block(32, 8, 1), grid = grid_for(p.out.w, p.y1 - p.y0);
-  if (format == 2) {
-    if (exact) { rcas_direct_kernel<float, true><<<grid, block, 0, s>>>(p); *name = "rcas_direct<f32,exact>"; }
-    else       { rcas_direct_kernel<float, false><<<grid, block, 0, s>>>(p); *name = "rcas_direct<f32,fast>"; }
-  } else {
-    if (exact) { rcas_direct_kernel<__half, true><<<grid, block, 0, s>>>(p); *name = "rcas_direct<f16io,exact>"; }
-    else       { rcas_direct_kernel<__half, false><<<grid, block, 0, s>>>(p); *name = "rcas_direct<f16io,fast>"; }
+  switch (format) {
+    case 1: launch_rcas_s<__half>(p, exact, s, grid, block); break;
+    case 2: launch_rcas_s<float>(p, exact, s, grid, block); break;
+    case 3: launch_rcas_s<Unorm8>(p, exact, s, grid, block); break;
+    case 4: launch_rcas_s<Unorm10>(p, exact, s, grid, block); break;
+    default: return cudaErrorInvalidValue;
   }
+  *name = direct_name("rcas", format, exact);
   return cudaGetLastError();
 }
 

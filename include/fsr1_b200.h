@@ -26,7 +26,9 @@
  *   - EASU taps are clamped to the edge of the input RESOURCE (linear/clamp sampler, FSR_Filter.cpp:48-53)
  *   - RCAS taps outside the image read 0 (D3D12 Load); FSR1_FLAG_RCAS_CLAMP selects clamp instead
  *   - fp32 images run the F algorithm in fp32; fp16 images run a packed-half implementation whose
- *     results stay within 1e-2 of the fp32 algorithm on the same (quantised) input
+ *     results stay within 1e-2 of the fp32 algorithm on the same (quantised) input; UNORM images (the
+ *     formats the sample renders into, FSR_Filter.cpp:72-73) run the F algorithm in fp32 on the D3D
+ *     unorm<->float conversions (c/(2^n-1); clamp, scale, +0.5, truncate)
  * All launch calls are asynchronous with respect to the host and allocate nothing
  * (fsr1_context_create and fsr1_upscale_host's first use are the only allocating calls).
  * Thread-safe for distinct contexts/streams.  Every function returns FSR1_OK or a negative fsr1 error;
@@ -52,7 +54,12 @@ enum {
   FSR1_ERR_NO_DEVICE = -5         /* no usable sm_100 device / driver                              */
 };
 
-enum { FSR1_FORMAT_RGBA16F = 1, FSR1_FORMAT_RGBA32F = 2 };
+enum {
+  FSR1_FORMAT_RGBA16F = 1,
+  FSR1_FORMAT_RGBA32F = 2,
+  FSR1_FORMAT_RGBA8_UNORM = 3,    /* 4 B/px, byte order R,G,B,A (DXGI_FORMAT_R8G8B8A8_UNORM)                      */
+  FSR1_FORMAT_RGB10A2_UNORM = 4   /* 4 B/px, bits 0-9 R, 10-19 G, 20-29 B, 30-31 A (DXGI_FORMAT_R10G10B10A2_UNORM) */
+};
 
 enum {
   FSR1_FLAG_RCAS_CLAMP = 1u << 0,   /* RCAS out-of-image taps clamp instead of reading 0               */

@@ -176,6 +176,60 @@ def test_rcas_denoise_and_alpha_passthrough_options(denoise, alpha):
                 assert np.array_equal(got[..., 3], img[..., 3]) and np.array_equal(href[..., 3], imh[..., 3])
 
 
+def _q(x, n):
+    """D3D float -> unorm: clamp, scale by 2^n-1, add 0.5, truncate (NaN -> 0)."""
+    s = np.float32((1 << n) - 1)
+    return (np.nan_to_num(np.clip(x, 0.0, 1.0), nan=0.0).astype(np.float32) * s + np.float32(0.5)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("shape", [(96, 54, 192, 108), (50, 20, 65, 26), (33, 17, 57, 31)])
+def test_unorm_formats_exact(shape):
+    """R8G8B8A8_UNORM / R10G10B10A2_UNORM images (what the sample renders into): fp32 F-path arithmetic between the D3D
+    unorm<->float conversions; with FSR1_FLAG_EXACT the stored integers equal quantise(oracle(dequantise(input)))."""
+    iw, ih, ow, oh = shape
+    rng = np.random.default_rng(5)
+    for bits in (8, 10):
+        s = np.float32((1 << bits) - 1)
+        raw = rng.integers(0, 1 << bits, size=(ih, iw, 4), dtype=np.uint32)
+        if bits == 10:
+            raw[..., 3] = rng.integers(0, 4, size=(ih, iw))
+        fin = (raw.astype(np.float32) / s).astype(np.float32)                     # c / (2^n - 1), correctly rounded
+        fin[..., 3] = raw[..., 3].astype(np.float32) / np.float32(255.0 if bits == 8 else 3.0)
+        e_want = ol.easu(fin, ow, oh)
+        def pack(q):
+            if bits == 8:
+                return torch.from_numpy(q.astype(np.uint8)).cuda()
+            w = (q[..., 0] | (q[..., 1] << 10) | (q[..., 2] << 20) | (q[..., 3] << 30)).astype(np.uint32)
+            return torch.from_numpy(w.view(np.int32)).cuda()
+        def unpack(t):
+            a = t.cpu().numpy()
+            if bits == 8:
+                return a.astype(np.uint32)
+            w = a.view(np.uint32)
+            return np.stack([w & 1023, (w >> 10) & 1023, (w >> 20) & 1023, w >> 30], axis=-1)
+        din = pack(raw)
+        dout = torch.zeros((oh, ow, 4), dtype=torch.uint8, device="cuda") if bits == 8 else torch.zeros((oh, ow), dtype=torch.int32, device="cuda")
+        api.easu(din, dout, api.easu_con(iw, ih, iw, ih, ow, oh), flags=api.FLAG_EXACT)
+        torch.cuda.synchronize()
+        assert api.last_kernel() == "easu_direct<unorm%d,exact>" % bits
+        got = unpack(dout)
+        want = np.concatenate([_q(e_want[..., :3], bits), np.full((oh, ow, 1), (1 << bits) - 1 if bits == 8 else 3, np.uint32)], axis=-1)
+        assert np.array_equal(got, want)
+        # RCAS on the quantised EASU output
+        mid = (want.astype(np.float32) / s).astype(np.float32)
+        mid[..., 3] = 1.0
+        r_want = ol.rcas(mid, ol.rcas_con(0.25))
+        rout = torch.zeros_like(dout)
+        api.rcas(dout, rout, api.rcas_con(0.25), flags=api.FLAG_EXACT)
+        torch.cuda.synchronize()
+        rw = np.concatenate([_q(r_want[..., :3], bits), np.full((oh, ow, 1), (1 << bits) - 1 if bits == 8 else 3, np.uint32)], axis=-1)
+        assert np.array_equal(unpack(rout), rw)
+        # default (contracted) arithmetic may move a value across a rounding boundary: at most one code value
+        api.easu(din, dout, api.easu_con(iw, ih, iw, ih, ow, oh))
+        torch.cuda.synchronize()
+        assert np.abs(unpack(dout).astype(np.int64) - want.astype(np.int64)).max() <= 1
+
+
 def test_precise_flag_fp32_math_on_fp16_storage():
     """FSR1_FLAG_PRECISE at 2x: packed-FFMA2 fp32 arithmetic on RGBA16F images; only the final rounding to half is left."""
     for gen in ("uniform", "structured"):
