@@ -225,10 +225,10 @@ def run_ours(args, rank, world, local_rank):
         tmps = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
         outs = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
         imgs = [(api.image(ins[i]), api.image(tmps[i]), api.image(outs[i])) for i in range(RING)]
+        prepared = [api.PreparedUpscale(a, t, b, econ1, rcon) for a, t, b in imgs]   # arguments marshalled once per buffer set
 
         def step(i):
-            a, t, b = imgs[i % RING]
-            api.upscale(a, t, b, econ1, rcon, stream=stream)
+            prepared[i % RING].launch(stream)
 
         def step_easu(i):
             a, t, _ = imgs[i % RING]

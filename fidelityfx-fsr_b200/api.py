@@ -96,6 +96,22 @@ def upscale(inp, tmp, out, econ, rcon, y0=0, y1=0, flags=0, stream=None):
                                        (ctypes.c_uint32 * 4)(*rcon), y0, y1, flags, _stream(stream)))
 
 
+class PreparedUpscale:
+    """fsr1_upscale with every argument marshalled once: the per-frame host cost is one foreign call.
+    (Streams of frames through fixed buffers — the sharded path, the bench — re-launch the same descriptors.)"""
+
+    def __init__(self, inp, tmp, out, econ, rcon, y0=0, y1=0, flags=0):
+        self._a, self._t, self._b = _as_img(inp), _as_img(tmp), _as_img(out)
+        self._econ, self._rcon = (ctypes.c_uint32 * 16)(*econ), (ctypes.c_uint32 * 4)(*rcon)
+        self._args = (ctypes.byref(self._a), ctypes.byref(self._t), ctypes.byref(self._b), self._econ, self._rcon, y0, y1, flags)
+        self._fn = _lib.lib().fsr1_upscale
+
+    def launch(self, stream=None):
+        rc = self._fn(*self._args, _stream(stream))
+        if rc:
+            _lib.check(rc)
+
+
 def last_kernel():
     return _lib.lib().fsr1_last_kernel_name().decode()
 

@@ -130,6 +130,7 @@ class ShardedUpscaler:
         self.tmp = torch.empty((e1 - e0, out_w, 4), dtype=dtype, device=device)
         self.out = torch.empty((y1 - y0, out_w, 4), dtype=dtype, device=device)
         self._graph = None
+        self._prepared = None
         import os
         self.halo_mode = os.environ.get("FSR1_HALO_MODE", "a2a")   # "p2p": batch_isend_irecv; "a2a": one all_to_all
 
@@ -169,12 +170,14 @@ class ShardedUpscaler:
             req.wait()
 
     def _launch(self, stream=None):
-        plan, rank = self.plan, self.rank
-        e0, _ = plan.easu_rows(rank)
-        y0, y1 = plan.out_rows(rank)
-        api.upscale(api.image(self.window, height=self.in_h, row0=self._win0), api.image(self.tmp, height=self.out_h, row0=e0),
-                    api.image(self.out, height=self.out_h, row0=y0), self.econ, self.rcon, y0=y0, y1=y1,
-                    flags=self.flags, stream=stream)
+        if self._prepared is None:
+            plan, rank = self.plan, self.rank
+            e0, _ = plan.easu_rows(rank)
+            y0, y1 = plan.out_rows(rank)
+            self._prepared = api.PreparedUpscale(
+                api.image(self.window, height=self.in_h, row0=self._win0), api.image(self.tmp, height=self.out_h, row0=e0),
+                api.image(self.out, height=self.out_h, row0=y0), self.econ, self.rcon, y0=y0, y1=y1, flags=self.flags)
+        self._prepared.launch(stream)
 
     def upscale(self, owned_rows=None, stream=None):
         """Upscale the frame whose slab is in self.owned (or in `owned_rows`, which is then copied in)."""

@@ -348,6 +348,22 @@ def test_slabs_compose(dt):
     assert torch.equal(torch.cat(parts), whole)
 
 
+def test_sharded_upscaler_single_rank_equals_plain_upscale():
+    """world = 1: the sharded path issues no communication and must give exactly the plain result (the N > 1 exchange
+    is covered on CPU over gloo, tests/test_sharding.py, and by bench.py --gpus N)."""
+    iw, ih, ow, oh = 160, 90, 320, 180
+    src = torch.from_numpy(F.to_half(F.structured(iw, ih, 15))).cuda()
+    up = F.ShardedUpscaler(iw, ih, ow, oh, 1, 0)
+    up.owned.copy_(src)
+    got = up.upscale().clone()
+    got2 = up.upscale().clone()          # second call re-launches the prepared descriptors
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    want = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    api.upscale(src, tmp, want, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got2, want)
+
+
 def test_host_frame_entry_point():
     iw, ih, ow, oh = 120, 68, 240, 136
     src = F.to_half(F.structured(iw, ih, 14))
