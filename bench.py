@@ -402,6 +402,10 @@ def run_ours(args, rank, world, local_rank):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use all host threads it can,
+    # so restore the default BEFORE the OpenMP runtime of the oracle libraries is loaded
+    if os.environ.get("WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     wl = WORKLOADS[args.workload]
     r = time_cpu(wl, steps=args.steps, warmup=max(args.warmup, 1), budget_s=100.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus,

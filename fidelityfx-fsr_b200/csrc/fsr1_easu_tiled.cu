@@ -616,11 +616,9 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   const size_t smem = pairs_smem_bytes(BW, BH);
   if (smem > 200 * 1024) return cudaErrorNotSupported;
   if (!make_tmap(&tmap, p.in, BW, BH)) return cudaErrorNotSupported;
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {  // per device and cheap: set on every launch that needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(easu_h_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   const int tiles_x = (p.out.w + kTileW - 1) / kTileW, n_tiles = tiles_x * ((p.y1 - p.y0 + kTileH - 1) / kTileH);
   int per_sm = 3;

@@ -69,3 +69,29 @@ def test_cpp_filter_mirror_compiles_and_links(tmp_path):
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", ROOT, str(src), "-o", str(exe), "-L", libdir, "-lfsr1_b200",
                            "-Wl,-rpath," + libdir])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_easu_input_rows_against_brute_force():
+    """fsr1_easu_input_rows (host logic, no GPU): first/last input row of an output row range = min/max tap row over
+    its pixels, in the kernels' float arithmetic, for the quality presets and random dynamic-resolution viewports."""
+    import numpy as np
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    cases = [(1080, 2160), (1440, 2160), (1661, 2160), (1270, 2160), (2160, 4320), (17, 31), (5, 40), (64, 64)]
+    cases += [(int(rng.integers(4, 3000)), 0) for _ in range(40)]
+    for in_h, out_h in cases:
+        if out_h == 0:
+            out_h = int(in_h * rng.uniform(1.0, 2.0))
+        vp_h = in_h if rng.random() < 0.5 else int(in_h * rng.uniform(0.5, 1.0)) or 1
+        con = (ctypes.c_uint32 * 16)(*F.api.easu_con(64, vp_h, 64, in_h, 128, out_h))
+        scale = np.array([con[1]], np.uint32).view(np.float32)[0]
+        off = np.array([con[3]], np.uint32).view(np.float32)[0]
+        for _ in range(6):
+            y0 = int(rng.integers(0, out_h))
+            y1 = int(rng.integers(y0 + 1, out_h + 1))
+            cells = np.floor((np.arange(y0, y1, dtype=np.float32) * scale).astype(np.float32) + off).astype(np.int64)
+            lo = int(np.clip(cells.min() - 1, 0, in_h - 1))
+            hi = int(np.clip(cells.max() + 2, 0, in_h - 1))
+            a, b = ctypes.c_uint32(), ctypes.c_uint32()
+            assert L.fsr1_easu_input_rows(con, in_h, y0, y1, ctypes.byref(a), ctypes.byref(b)) == 0
+            assert (a.value, b.value) == (lo, hi), (in_h, out_h, vp_h, y0, y1)
