@@ -603,6 +603,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
       *name = variant == 3 ? "easu_h_quad2x_ws<4+1w,5/sm,tma2>" : "easu_h_quad2x_ws<4+1w,4/sm,tma2>";
       return cudaGetLastError();
     }
+    if (variant == 5) return launch(easu_h_quad2x_kernel<4, 7>, 4, 7, "easu_h_quad2x<4w,7/sm,tma2>");
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");

@@ -95,3 +95,22 @@ def test_easu_input_rows_against_brute_force():
             a, b = ctypes.c_uint32(), ctypes.c_uint32()
             assert L.fsr1_easu_input_rows(con, in_h, y0, y1, ctypes.byref(a), ctypes.byref(b)) == 0
             assert (a.value, b.value) == (lo, hi), (in_h, out_h, vp_h, y0, y1)
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    exe = tmp_path / "fsr1_demo"
+    libdir = os.path.join(ROOT, "fidelityfx-fsr_b200", "lib")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(ROOT, "examples", "fsr1_demo.c"), "-o", str(exe), "-L", libdir, "-lfsr1_b200",
+                           "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_plain_c_host_program_builds_against_the_abi(tmp_path):
+    """examples/fsr1_demo.c: C99, the reference's include lines (served by include/compat), one fsr1_upscale call."""
+    import subprocess
+    import torch
+    exe = _build_c_demo(tmp_path)
+    if not torch.cuda.is_available():
+        assert subprocess.call([str(exe)], stderr=subprocess.DEVNULL) == 2      # "no CUDA device": loud, no fallback

@@ -320,16 +320,18 @@ def test_dynamic_resolution_viewport_and_offset():
         assert np.abs(goth - ol.easu(F.to_half(src).astype(np.float32), ow, oh, con)).max() <= TOL16
 
 
+@pytest.mark.parametrize("shape", [(64, 60, 128, 120), (64, 60, 96, 90), (70, 50, 91, 65)])
 @pytest.mark.parametrize("dt", [np.float16, np.float32])
-def test_slabs_compose(dt):
-    """Row windows (the multi-GPU slabs) give exactly the bytes of the whole-frame run."""
-    iw, ih, ow, oh = 64, 60, 128, 120
+def test_slabs_compose(dt, shape):
+    """Row windows (the multi-GPU slabs) give exactly the bytes of the whole-frame run — for the 2x kernels, the
+    generic kernel (1.5x, 1.3x) and the direct kernels alike."""
+    iw, ih, ow, oh = shape
     src = F.uniform(iw, ih, 13).astype(dt)
     tdt = torch.float16 if dt == np.float16 else torch.float32
     econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
     full_in = dev(src)
-    tmp = torch.zeros((oh, ow, 4), dtype=tdt, device="cuda")
-    whole = torch.zeros((oh, ow, 4), dtype=tdt, device="cuda")
+    tmp = empty_like_image(oh, ow, tdt)
+    whole = empty_like_image(oh, ow, tdt)
     api.upscale(full_in, tmp, whole, econ, rcon)
     parts = []
     for world in (3,):
@@ -338,9 +340,9 @@ def test_slabs_compose(dt):
             n0, n1 = plan.needed_in_rows(r)
             e0, e1 = plan.easu_rows(r)
             y0, y1 = plan.out_rows(r)
-            win = full_in[n0:n1].contiguous()
-            t = torch.zeros((e1 - e0, ow, 4), dtype=tdt, device="cuda")
-            o = torch.zeros((y1 - y0, ow, 4), dtype=tdt, device="cuda")
+            win = full_in[n0:n1]
+            t = empty_like_image(e1 - e0, ow, tdt)
+            o = empty_like_image(y1 - y0, ow, tdt)
             api.upscale(api.image(win, height=ih, row0=n0), api.image(t, height=oh, row0=e0),
                         api.image(o, height=oh, row0=y0), econ, rcon, y0=y0, y1=y1)
             parts.append(o)
@@ -362,6 +364,21 @@ def test_sharded_upscaler_single_rank_equals_plain_upscale():
     api.upscale(src, tmp, want, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25))
     torch.cuda.synchronize()
     assert torch.equal(got, want) and torch.equal(got2, want)
+
+
+def test_plain_c_host_program(tmp_path):
+    """examples/fsr1_demo.c run on the GPU; its checksum against the oracle on the same gradient frame."""
+    import subprocess
+    from test_abi import _build_c_demo
+    out = subprocess.check_output([str(_build_c_demo(tmp_path))]).decode()
+    assert "easu" in out or "rcas" in out
+    rw, rh, dw, dh = 640, 360, 1280, 720
+    y, x = np.mgrid[0:rh, 0:rw]
+    frame = np.stack([x / np.float32(rw), y / np.float32(rh), (((x // 16 + y // 16) & 1) == 1).astype(np.float32),
+                      np.ones((rh, rw), np.float32)], axis=-1).astype(np.float32)
+    want = ol.rcas(ol.easu(frame, dw, dh), ol.rcas_con(0.25))[..., :3].astype(np.float64).sum()
+    got = float(out.split("checksum")[1].split(",")[0])
+    assert abs(got - want) <= 1e-6 * want + 0.5
 
 
 def test_host_frame_entry_point():
