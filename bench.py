@@ -226,9 +226,16 @@ def run_ours(args, rank, world, local_rank):
         outs = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
         imgs = [(api.image(ins[i]), api.image(tmps[i]), api.image(outs[i])) for i in range(RING)]
         prepared = [api.PreparedUpscale(a, t, b, econ1, rcon) for a, t, b in imgs]   # arguments marshalled once per buffer set
+        pipe = None if args.no_pipeline else api.FramePipeline(imgs, econ1, rcon, device=dev)
+
+        def step_seq(i):
+            prepared[i % RING].launch(stream)
 
         def step(i):
-            prepared[i % RING].launch(stream)
+            if pipe is None:
+                step_seq(i)
+            else:
+                pipe.submit(i % RING)      # RCAS of frame i overlaps EASU of frame i+1 (two streams)
 
         def step_easu(i):
             a, t, _ = imgs[i % RING]
@@ -282,15 +289,19 @@ def run_ours(args, rank, world, local_rank):
         total_out_px = ow * H_out
         halo = ups[0].plan.halo_bytes(rank, iw, bpp)
 
-    def timed(fn, n):
+    def timed(fn, n, pre=None, post=None):
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        if pre:
+            pre()
         for i in range(n):
             fn(i)
+        if post:
+            post()
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -307,7 +318,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = api.launch_count()
-    ms = timed(step, K)
+    piped = world == 1 and pipe is not None
+    ms = timed(step, K, pre=(lambda: pipe.begin(stream)) if piped else None, post=(lambda: pipe.end(stream)) if piped else None)
     launches = api.launch_count() - launches0
     if world > 1 and args.graph:
         launches = 2 * K  # each replayed graph holds this library's two kernels (EASU, RCAS), recorded at capture
@@ -316,7 +328,12 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_src = load_peaks()
     kernels, roofline = {}, None
+    latency_ms = None
     if world == 1:
+        if piped:
+            for i in range(W):
+                step_seq(i)
+            latency_ms = timed(step_seq, K) / K      # one frame at a time on one stream: EASU then RCAS, no overlap
         Pin, Pout = iw * ih, ow * oh
         alg = {"easu": bpp * (Pin + Pout), "rcas": bpp * 2 * Pout}
         names = {}
@@ -386,6 +403,12 @@ def run_ours(args, rank, world, local_rank):
                            world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else "halo exchange of frame i+1 overlapped with frame i on a second stream"))},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if world == 1:
+            line["config"]["pipelining"] = ("two CUDA streams: RCAS of frame i overlaps EASU of frame i+1 (api.FramePipeline)"
+                                            if piped else "none: EASU then RCAS of each frame on one stream")
+            if latency_ms is not None:
+                line["unpipelined_ms_per_step"] = latency_ms
+                line["unpipelined_value"] = total_out_px / (latency_ms * 1e-3) / 1e6
         if roofline:
             line["roofline"] = roofline
             line["kernels"] = kernels
@@ -428,6 +451,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-4k-fp16", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pipeline", action="store_true", help="N=1: run EASU and RCAS of each frame back to back on one stream (no frame overlap)")
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")

@@ -583,8 +583,11 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
     const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
+    static int cap = -1;  // FSR1_EASU_CTAS_PER_SM: leave room on every SM for a concurrently running kernel (frame pipelining)
+    if (cap < 0) { const char* e = getenv("FSR1_EASU_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }
     auto launch = [&](auto kernel, int nw, int per_sm, const char* nm) -> cudaError_t {
       const int cy = 2 * nw;
+      if (cap > 0 && cap < per_sm) per_sm = cap;
       if (!make_tmap(&tmap, p.in, kQBW, cy + 3)) return cudaErrorNotSupported;
       const int tiles_y = (m_last - m_first + 1 + cy - 1) / cy, n_tiles = tiles_x * tiles_y;
       const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
