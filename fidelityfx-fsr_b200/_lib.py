@@ -9,13 +9,13 @@ LIB_PATH = os.path.join(HERE, "lib", "libfsr1_b200.so")
 FSR1_OK = 0
 FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_RGB10A2_UNORM = 1, 2, 3, 4
 FLAG_RCAS_CLAMP, FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_H_REFERENCE, FLAG_PRECISE = 1, 2, 4, 8, 16, 32
-FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA = 64, 128
+FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE = 64, 128, 256
 
 # every symbol include/fsr1_b200.h declares
 SYMBOLS = ["fsr1_easu", "fsr1_rcas", "fsr1_easu_input_rows", "fsr1_upscale", "fsr1_context_create",
            "fsr1_context_destroy", "fsr1_context_upscale", "fsr1_context_upscale_host", "fsr1_easu_con",
            "fsr1_easu_con_offset", "fsr1_rcas_con", "fsr1_abi_version", "fsr1_error_string",
-           "fsr1_last_cuda_error", "fsr1_launch_count", "fsr1_last_kernel_name"]
+           "fsr1_last_cuda_error", "fsr1_launch_count", "fsr1_last_kernel_name", "fsr1_srtm", "fsr1_lfga", "fsr1_tepd"]
 
 
 class Image(ctypes.Structure):
@@ -57,6 +57,9 @@ def lib():
     L.fsr1_easu_con_offset.restype = None
     L.fsr1_rcas_con.argtypes = [u32p, f32]
     L.fsr1_rcas_con.restype = None
+    L.fsr1_srtm.argtypes = [imgp, imgp, ctypes.c_int, u32, u32, vp]
+    L.fsr1_lfga.argtypes = [imgp, imgp, imgp, f32, u32, u32, vp]
+    L.fsr1_tepd.argtypes = [imgp, imgp, imgp, ctypes.c_int, u32, u32, u32, vp]
     L.fsr1_error_string.restype = ctypes.c_char_p
     L.fsr1_error_string.argtypes = [ctypes.c_int]
     L.fsr1_last_kernel_name.restype = ctypes.c_char_p

@@ -9,6 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import FORMAT_RGB10A2_UNORM, FORMAT_RGBA8_UNORM  # noqa: F401
+from ._lib import FLAG_OUTPUT_SQUARE  # noqa: F401
 from ._lib import (FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_H_REFERENCE, FLAG_NO_RCAS, FLAG_PRECISE, FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_RCAS_CLAMP, FORMAT_RGBA16F,  # noqa: F401
                    FORMAT_RGBA32F, Fsr1Error, Image)
 
@@ -94,6 +95,28 @@ def upscale(inp, tmp, out, econ, rcon, y0=0, y1=0, flags=0, stream=None):
     a, t, b = _as_img(inp), _as_img(tmp), _as_img(out)
     _lib.check(_lib.lib().fsr1_upscale(ctypes.byref(a), ctypes.byref(t), ctypes.byref(b), (ctypes.c_uint32 * 16)(*econ),
                                        (ctypes.c_uint32 * 4)(*rcon), y0, y1, flags, _stream(stream)))
+
+
+def srtm(inp, out, inverse=False, y0=0, y1=0, stream=None):
+    """FsrSrtmF / FsrSrtmInvF (ffx_fsr1.h:1044,1046) over rows [y0,y1); `out` may be `inp` (in place)."""
+    a, b = _as_img(inp), _as_img(out)
+    _lib.check(_lib.lib().fsr1_srtm(ctypes.byref(a), ctypes.byref(b), 1 if inverse else 0, y0, y1, _stream(stream)))
+
+
+def lfga(inp, grain, out, amount, y0=0, y1=0, stream=None):
+    """FsrLfgaF (ffx_fsr1.h:1014): film grain from the tiled RGB `grain` image ({-0.5..0.5})."""
+    a, g, b = _as_img(inp), _as_img(grain), _as_img(out)
+    _lib.check(_lib.lib().fsr1_lfga(ctypes.byref(a), ctypes.byref(g), ctypes.byref(b), ctypes.c_float(amount), y0, y1,
+                                    _stream(stream)))
+
+
+def tepd(inp, out, bits, frame=0, dither=None, y0=0, y1=0, stream=None):
+    """FsrTepdC8F / FsrTepdC10F (ffx_fsr1.h:1100-1126); dither None -> FsrTepdDitF(pixel, frame), else the .w channel of
+    the tiled `dither` image.  `out` may be a UNORM image (uint8 [H,W,4] for 8 bits, int32 [H,W] for 10)."""
+    a, b = _as_img(inp), _as_img(out)
+    d = _as_img(dither) if dither is not None else None
+    _lib.check(_lib.lib().fsr1_tepd(ctypes.byref(a), ctypes.byref(d) if d is not None else None, ctypes.byref(b), bits,
+                                    frame, y0, y1, _stream(stream)))
 
 
 class PreparedUpscale:

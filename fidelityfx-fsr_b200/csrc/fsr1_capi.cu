@@ -66,6 +66,40 @@ bool window_holds(const fsr1_image* im, int first, int last) {  // logical rows 
   return first >= (int)im->row0 && last < (int)(im->row0 + im->rows);
 }
 
+// the Sample.x hook: `c *= c` in place on the rows the last pass wrote (a separate streaming pass)
+int square_rows(const fsr1_image* img, uint32_t y0, uint32_t y1, cudaStream_t s) {
+  const ImgView v = view_of(img);
+  const char* name = "";
+  cudaError_t e = launch_pointwise(6, v, (int)img->format, v, (int)img->format, nullptr, 0, 0.0f, 0u, (int)y0, (int)y1, s, &name);
+  if (e != cudaSuccess) return cuda_fail(e);
+  t_last_kernel = name;
+  g_launches.fetch_add(1);
+  return FSR1_OK;
+}
+
+int pointwise(int op, const fsr1_image* in, const fsr1_image* aux, const fsr1_image* out, float amount, uint32_t frame,
+              uint32_t y0, uint32_t y1, void* stream) {
+  int rc;
+  if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
+  if (aux && (rc = check_image(aux)) != FSR1_OK) return rc;
+  if (aux && (aux->row0 != 0 || aux->rows != aux->height)) return FSR1_ERR_INVALID_ARGUMENT;  // tiles are whole images
+  if (in->width != out->width || in->height != out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (y1 == 0) y1 = out->height;
+  if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!window_holds(out, (int)y0, (int)y1 - 1) || !window_holds(in, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
+  const ImgView vi = view_of(in), vo = view_of(out);
+  ImgView va;
+  if (aux) va = view_of(aux);
+  const char* name = "";
+  cudaError_t e = launch_pointwise(op, vi, (int)in->format, vo, (int)out->format, aux ? &va : nullptr, aux ? (int)aux->format : 0,
+                                   amount, frame, (int)y0, (int)y1, static_cast<cudaStream_t>(stream), &name);
+  if (e == cudaErrorNotSupported) return FSR1_ERR_UNSUPPORTED;
+  if (e != cudaSuccess) return cuda_fail(e);
+  t_last_kernel = name;
+  g_launches.fetch_add(1);
+  return FSR1_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -144,6 +178,7 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;
   g_launches.fetch_add(1);
+  if (flags & FSR1_FLAG_OUTPUT_SQUARE) return square_rows(out, y0, y1, s);
   return FSR1_OK;
 }
 
@@ -187,6 +222,7 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;
   g_launches.fetch_add(1);
+  if (flags & FSR1_FLAG_OUTPUT_SQUARE) return square_rows(out, y0, y1, s);
   return FSR1_OK;
 }
 
@@ -198,9 +234,27 @@ int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* 
   if (!tmp) return FSR1_ERR_INVALID_ARGUMENT;
   // EASU also produces the one-row apron RCAS reads, so a row slab needs no second exchange
   const uint32_t e0 = y0 == 0 ? 0 : y0 - 1, e1 = y1 >= out->height ? out->height : y1 + 1;
-  int rc = fsr1_easu(in, tmp, easu_con, e0, e1, flags, stream);
+  int rc = fsr1_easu(in, tmp, easu_con, e0, e1, flags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, stream);  // last pass only
   if (rc != FSR1_OK) return rc;
   return fsr1_rcas(tmp, out, rcas_con, y0, y1, flags, stream);
+}
+
+// ---- pointwise companions ------------------------------------------------------------------------------
+int fsr1_srtm(const fsr1_image* in, const fsr1_image* out, int inverse, uint32_t y0, uint32_t y1, void* stream) {
+  return pointwise(inverse ? 2 : 1, in, nullptr, out, 0.0f, 0u, y0, y1, stream);
+}
+
+int fsr1_lfga(const fsr1_image* in, const fsr1_image* grain, const fsr1_image* out, float amount, uint32_t y0,
+              uint32_t y1, void* stream) {
+  if (!grain) return FSR1_ERR_INVALID_ARGUMENT;
+  if (grain->format != FSR1_FORMAT_RGBA16F && grain->format != FSR1_FORMAT_RGBA32F) return FSR1_ERR_UNSUPPORTED;  // signed values
+  return pointwise(3, in, grain, out, amount, 0u, y0, y1, stream);
+}
+
+int fsr1_tepd(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* out, int bits, uint32_t frame,
+              uint32_t y0, uint32_t y1, void* stream) {
+  if (bits != 8 && bits != 10) return FSR1_ERR_INVALID_ARGUMENT;
+  return pointwise(bits == 8 ? 4 : 5, in, dither, out, 0.0f, frame, y0, y1, stream);
 }
 
 // ---- context --------------------------------------------------------------------------------------

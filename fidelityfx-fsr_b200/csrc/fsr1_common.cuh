@@ -157,4 +157,8 @@ cudaError_t launch_rcas_f32_packed(const RcasParams& p, cudaStream_t s, const ch
 cudaError_t launch_easu_href(const EasuParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_href(const RcasParams& p, cudaStream_t s, const char** name);
 
+// Pointwise companions (fsr1_pointwise.cu): op 1 SRTM, 2 SRTM inverse, 3 LFGA, 4 TEPD 8 bit, 5 TEPD 10 bit, 6 square.
+cudaError_t launch_pointwise(int op, const ImgView& in, int in_format, const ImgView& out, int out_format, const ImgView* aux,
+                             int aux_format, float amount, uint32_t frame, int y0, int y1, cudaStream_t s, const char** name);
+
 }  // namespace fsr1

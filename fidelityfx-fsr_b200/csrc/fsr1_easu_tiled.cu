@@ -63,6 +63,14 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
   return __hmul2(wb, wa);
 }
 
+// the same without the distance clamp, for taps that provably never reach it (see quad_pair<.., 1>)
+__device__ __forceinline__ __half2 tap_weight_unclamped(__half2 d2, __half2 lob) {
+  const __half2 wb = __hfma2(__hfma2(h2c(0.25f), d2, h2c(-1.25f)), d2, h2c(1.0f));
+  __half2 wa = __hfma2(lob, d2, h2c(-1.0f));
+  wa = __hmul2(wa, wa);
+  return __hmul2(wb, wa);
+}
+
 // =======================================================================================================
 //  generic kernel: any scale, lane = pixel pair (2*lane, 2*lane+1), rows warp and warp+8 of a 64x16 tile
 // =======================================================================================================
@@ -298,7 +306,11 @@ template <int NW> struct QuadCfg {
 
 // One pixel pair (A: px=.25, B: px=.75) of the quad; kBottom selects py=.75.  t = the 12 taps (RG,BA);
 // every tap offset is a constant, so d2 is three half2 FMAs against immediates.
-template <bool kBottom>
+// kTap = 1 (default; kTap = 0 is FSR1_EASU_QUAD_VARIANT=2, 3 % slower on B200): rows 1 and 2 (four taps each) use the factored form
+// d2 = ox (qa ox + qb oy) + qc oy^2 with the row terms qb oy, qc oy^2 hoisted (10 instead of 12 half2 ops per row), and
+// the four nearest taps f g j k skip the min(d2, clp): at exactly 2x their offsets are <= .75 per axis, so
+// d2 <= 1.125 len2.x^2 (1 + eps) < clp = 1/lob for every len in [0,1] (1.24 (1 + .56 len)^2 vs .94 / (.5 - .29 len)).
+template <bool kBottom, int kTap>
 __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& sA, const Shape& sB, __half2 mnR,
                                           __half2 mnG, __half2 mnB, __half2 mxR, __half2 mxG, __half2 mxB,
                                           uint2& outA, uint2& outB) {
@@ -321,10 +333,32 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
     aB = __hfma2(__low2half2(ba), w, aB);                                                                   \
     aW = __hadd2(aW, w);                                                                                    \
   }
+#define FSR1_QTAP_ROW(R, K, INNER)                                                                          \
+  {                                                                                                         \
+    constexpr float oxA = (float)((K)-1) - 0.25f, oxB = (float)((K)-1) - 0.75f;                               \
+    const __half2 ox = __floats2half2_rn(oxA, oxB);                                                         \
+    const __half2 d2 = __hfma2(__hfma2(qa, ox, rowB##R), ox, rowC##R);                                       \
+    const __half2 w = (INNER) ? tap_weight_unclamped(d2, lob) : tap_weight(d2, lob, clp);                   \
+    const __half2 rg = u2h2(t[R][K].x), ba = u2h2(t[R][K].y);                                               \
+    aR = __hfma2(__low2half2(rg), w, aR);                                                                   \
+    aG = __hfma2(__high2half2(rg), w, aG);                                                                  \
+    aB = __hfma2(__low2half2(ba), w, aB);                                                                   \
+    aW = __hadd2(aW, w);                                                                                    \
+  }
   // far taps first, near taps (f g j k, the large weights) last: less rounding error in the half accumulators
-  FSR1_QTAP(0, 1) FSR1_QTAP(0, 2) FSR1_QTAP(1, 0) FSR1_QTAP(1, 3)
-  FSR1_QTAP(2, 0) FSR1_QTAP(2, 3) FSR1_QTAP(3, 1) FSR1_QTAP(3, 2)
-  FSR1_QTAP(1, 1) FSR1_QTAP(1, 2) FSR1_QTAP(2, 1) FSR1_QTAP(2, 2)
+  if (kTap == 0) {
+    FSR1_QTAP(0, 1) FSR1_QTAP(0, 2) FSR1_QTAP(1, 0) FSR1_QTAP(1, 3)
+    FSR1_QTAP(2, 0) FSR1_QTAP(2, 3) FSR1_QTAP(3, 1) FSR1_QTAP(3, 2)
+    FSR1_QTAP(1, 1) FSR1_QTAP(1, 2) FSR1_QTAP(2, 1) FSR1_QTAP(2, 2)
+  } else {
+    constexpr float oy1 = 0.0f - py, oy2 = 1.0f - py;
+    const __half2 rowB1 = __hmul2(qb, h2c(oy1)), rowC1 = __hmul2(qc, h2c(oy1 * oy1));
+    const __half2 rowB2 = __hmul2(qb, h2c(oy2)), rowC2 = __hmul2(qc, h2c(oy2 * oy2));
+    FSR1_QTAP(0, 1) FSR1_QTAP(0, 2) FSR1_QTAP_ROW(1, 0, false) FSR1_QTAP_ROW(1, 3, false)
+    FSR1_QTAP_ROW(2, 0, false) FSR1_QTAP_ROW(2, 3, false) FSR1_QTAP(3, 1) FSR1_QTAP(3, 2)
+    FSR1_QTAP_ROW(1, 1, true) FSR1_QTAP_ROW(1, 2, true) FSR1_QTAP_ROW(2, 1, true) FSR1_QTAP_ROW(2, 2, true)
+  }
+#undef FSR1_QTAP_ROW
 #undef FSR1_QTAP
   const float2 aWf = __half22float2(aW);
   const __half2 r = __floats2half2_rn(rcp_approx(aWf.x), rcp_approx(aWf.y));
@@ -338,6 +372,7 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
 
 // Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
 // k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
+template <int kTap = 0>
 __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __restrict__ tile, const float4* __restrict__ S,
                                           int gx0, int gy0, int lane, int r) {
   const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
@@ -372,14 +407,14 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
     if (rowT) {
       const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
       const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
-      quad_pair<false>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<false, kTap>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
     }
     if (rowB) {
       const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
       const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
-      quad_pair<true>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<true, kTap>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
     }
@@ -392,7 +427,7 @@ template <int NW> struct __align__(128) QuadSmem {
   uint64_t bar[2];
 };
 
-template <int NW, int MINB>
+template <int NW, int MINB, int kTap = 0>
 __global__ void __launch_bounds__(NW * 32, MINB)
 easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
                      const int n_tiles, const int mbase) {
@@ -446,7 +481,7 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     __syncthreads();
 
 #pragma unroll 1
-    for (int q = 0; q < 2; q++) quad_cell(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+    for (int q = 0; q < 2; q++) quad_cell<kTap>(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
     __syncthreads();  // L, S and this tile buffer are free again
   }
 }
@@ -578,8 +613,10 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   CUtensorMap tmap;
 
   if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
-    static int variant = -1;  // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6)
-    if (variant < 0) { const char* e = getenv("FSR1_EASU_QUAD_VARIANT"); variant = e ? atoi(e) : 2; }
+    // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
+    // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance)
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("FSR1_EASU_QUAD_VARIANT"); variant = e ? atoi(e) : 6; }
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
     const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
@@ -607,9 +644,10 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
       return cudaGetLastError();
     }
     if (variant == 5) return launch(easu_h_quad2x_kernel<4, 7>, 4, 7, "easu_h_quad2x<4w,7/sm,tma2>");
+    if (variant == 2) return launch(easu_h_quad2x_kernel<4, 6, 0>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,plain>");
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
-    return launch(easu_h_quad2x_kernel<4, 6>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");
+    return launch(easu_h_quad2x_kernel<4, 6, 1>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");
   }
 
   if (!(p.c0x > 0.0f && p.c0x <= 1.0f && p.c0y > 0.0f && p.c0y <= 1.0f)) return cudaErrorNotSupported;  // upscaling only

@@ -20,7 +20,7 @@
 
 namespace fsr1 {
 
-constexpr int kWarps = 8;   // warps per CTA, stacked vertically: CTA = 60 x (8*kRows) output pixels (kRows = rows walked by one lane)
+constexpr int kWarps = 8;   // warps per CTA of the 8-warp variants, stacked vertically: CTA = 60 x (kNW*kRows) output pixels (kRows = rows walked by one lane; default kNW = 4)
 constexpr int kSpan = 60;   // output pixels per warp per row (lanes 1..30)
 
 struct Row3 { __half2 r, g, b; };  // (pixel0, pixel1) per channel
@@ -143,12 +143,12 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
   }
 }
 
-template <bool kClamp, bool kNewton, int kRows>
-__global__ void __launch_bounds__(32 * kWarps) rcas_h_packed_kernel(const RcasParams p) {
+template <bool kClamp, bool kNewton, int kRows, int kNW = kWarps>
+__global__ void __launch_bounds__(32 * kNW) rcas_h_packed_kernel(const RcasParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kSpan - 2;  // even -> every lane's pair is 16-byte aligned
   const int x = x0 + lane * 2;
-  const int ys = p.y0 + (blockIdx.y * kWarps + warp) * kRows;
+  const int ys = p.y0 + (blockIdx.y * kNW + warp) * kRows;
   if (ys >= p.y1) return;  // whole warp
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kRows < p.in.h && ys + kRows <= p.y1;
   if (interior)
@@ -161,11 +161,18 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
-  static int variant = -1;  // development knob: FSR1_RCAS_VARIANT = 0 (4 rows/lane, MUFU), 1 (4 rows, Newton), 2 (8 rows/lane, MUFU)
-  if (variant < 0) { const char* e = getenv("FSR1_RCAS_VARIANT"); variant = e ? atoi(e) : 0; }
-  const int rows_per_cta = kWarps * (variant == 2 ? 8 : 4);
+  // development knob: FSR1_RCAS_VARIANT = 0 (8-warp CTAs, 4 rows/lane, MUFU), 1 (4 rows, Newton), 2 (8 rows/lane, MUFU),
+  // 3 = default (as 0 with 4-warp CTAs: same kernel time, but the smaller CTA starts earlier in the tail of the
+  // preceding EASU and shares SMs with it when frames are pipelined: 92.1 -> 90.7 us per frame back to back)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("FSR1_RCAS_VARIANT"); variant = e ? atoi(e) : 3; }
+  const int rows_per_cta = (variant == 3 ? 4 : kWarps) * (variant == 2 ? 8 : 4);
   const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + rows_per_cta - 1) / rows_per_cta, 1);
-  if (variant == 1) {
+  if (variant == 3) {
+    if (p.clamp) rcas_h_packed_kernel<true, false, 4, 4><<<grid, 32 * 4, 0, s>>>(p);
+    else rcas_h_packed_kernel<false, false, 4, 4><<<grid, 32 * 4, 0, s>>>(p);
+    *name = "rcas_h_packed<2px,4rows,shfl60,mufu>";
+  } else if (variant == 1) {
     if (p.clamp) rcas_h_packed_kernel<true, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
     else rcas_h_packed_kernel<false, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
     *name = "rcas_h_packed<2px,4rows,shfl60,newton>";
@@ -176,7 +183,7 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
   } else {
     if (p.clamp) rcas_h_packed_kernel<true, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
     else rcas_h_packed_kernel<false, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
-    *name = "rcas_h_packed<2px,4rows,shfl60,mufu>";
+    *name = "rcas_h_packed<2px,4rows,shfl60,mufu,8w>";
   }
   return cudaGetLastError();
 }

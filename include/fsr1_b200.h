@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FSR1_ABI_VERSION 1
+#define FSR1_ABI_VERSION 2
 
 enum {
   FSR1_OK = 0,
@@ -71,6 +71,8 @@ enum {
                                        (EASU at exactly 2x: packed FFMA2 taps); ~10x closer to the fp32 algorithm */
   FSR1_FLAG_RCAS_DENOISE = 1u << 6, /* the reference's FSR_RCAS_DENOISE compile-time option (ffx_fsr1.h:651,731-763)      */
   FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA = 1u << 7, /* FSR_RCAS_PASSTHROUGH_ALPHA (:648,688-702): output alpha = input alpha */
+  FSR1_FLAG_OUTPUT_SQUARE = 1u << 8, /* the sample's Sample.x hook (sample/src/DX12/FSR_Pass.hlsl:78-79,93-94): `c *= c` on the
+                                       output of the LAST pass (gamma 2.0, as produced by TEPD, back to linear)      */
   FSR1_FLAG_H_REFERENCE = 1u << 4   /* fp16 images only: the literal FsrEasuH / FsrRcasH arithmetic (packed-half
                                        algorithm, half magic numbers, per-operation half rounding), bit-identical
                                        to the reference's H source; a parity path, slower and LESS accurate than
@@ -124,6 +126,24 @@ int fsr1_context_upscale(fsr1_context* ctx, const void* in_dev, uint64_t in_pitc
 /* Host-resident frames (pinned memory recommended): H2D copy, EASU, RCAS, D2H copy on `stream`. */
 int fsr1_context_upscale_host(fsr1_context* ctx, const void* in_host, uint64_t in_pitch, void* out_host,
                               uint64_t out_pitch, float sharpness_stops, uint32_t flags, void* stream);
+
+/* ---- pointwise companions of the scaling path (ffx-fsr/ffx_fsr1.h:986-1199) ----------------------
+ * The passes the sample runs either side of EASU/RCAS, as whole-image streaming kernels over rows [y0,y1)
+ * (y1 == 0: to the last row).  `in` and `out` have the same logical size and may be the same image (in place).
+ * Arithmetic is fp32 with separate roundings for every storage format: RGBA32F results are bit-identical to the
+ * reference's F functions, other formats round that result once on store.  Alpha is carried through.
+ *   fsr1_srtm   FsrSrtmF (inverse == 0) / FsrSrtmInvF (inverse != 0)   ffx_fsr1.h:1044,1046
+ *   fsr1_lfga   FsrLfgaF: c += (grain * amount) * min(1 - c, c)         ffx_fsr1.h:1014
+ *               `grain` = RGB image of {-0.5..0.5} values (float formats), tiled over the frame with wrap addressing
+ *   fsr1_tepd   FsrTepdC8F (bits == 8) / FsrTepdC10F (bits == 10)       ffx_fsr1.h:1100-1126
+ *               dither == NULL: FsrTepdDitF(pixel, frame) (ffx_fsr1.h:1086-1095); else the saturated .w channel of the
+ *               tiled `dither` image (sample/src/DX12/FSR_Tonemapping.hlsl:87).  `out` may be the same format as `in`
+ *               or, from a float image, RGBA8_UNORM (bits 8) / RGB10A2_UNORM (bits 10): the code values themselves. */
+int fsr1_srtm(const fsr1_image* in, const fsr1_image* out, int inverse, uint32_t y0, uint32_t y1, void* stream);
+int fsr1_lfga(const fsr1_image* in, const fsr1_image* grain, const fsr1_image* out, float amount, uint32_t y0,
+              uint32_t y1, void* stream);
+int fsr1_tepd(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* out, int bits, uint32_t frame,
+              uint32_t y0, uint32_t y1, void* stream);
 
 /* ---- constants through the ABI (for FFIs that cannot include fsr1_host.h) ---------------------- */
 void fsr1_easu_con(uint32_t con[16], float in_viewport_w, float in_viewport_h, float in_size_w, float in_size_h,

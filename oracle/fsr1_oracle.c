@@ -17,6 +17,10 @@
  *   fsr1o_rcas_f32             FsrRcasF                        ffx-fsr/ffx_fsr1.h:684-769
  *   fsr1o_easu_h16 / fsr1o_rcas_h16   FsrEasuH / FsrRcasH      ffx-fsr/ffx_fsr1.h:452-593, 782-866
  *     (half approximations ffx-fsr/ffx_a.h:1808,1814,1820)
+ *   fsr1o_lfga_f32             FsrLfgaF                        ffx-fsr/ffx_fsr1.h:1014
+ *   fsr1o_srtm_f32             FsrSrtmF / FsrSrtmInvF          ffx-fsr/ffx_fsr1.h:1044-1046
+ *   fsr1o_tepd_dit / fsr1o_tepd_f32   FsrTepdDitF / FsrTepdC8F / FsrTepdC10F   ffx-fsr/ffx_fsr1.h:1086-1126
+ *     (AGtZeroF1 = saturate(m * +INF) ffx-fsr/ffx_a.h:1499; APrxMedRcpF3 :1854)
  * Addressing follows the sample's shader wrapper: gather4 through a linear/clamp sampler
  * (sample/src/DX12/FSR_Pass.hlsl:39-41, FSR_Filter.cpp:48-53) = per-texel clamp-to-edge of the
  * integer tap coordinate; RCAS uses integer Load, out of bounds -> 0 (D3D12) or clamp (switch).
@@ -384,3 +388,66 @@ void fsr1o_lcg_fill(float* dst, size_t n, uint32_t seed) {
 /* IEEE round-to-nearest-even conversions for building RGBA16F test frames. */
 void fsr1o_f32_to_f16_rne(const float* src, uint16_t* dst, size_t n) { for (size_t i = 0; i < n; i++) dst[i] = h2w((h16)src[i]); }
 void fsr1o_f16_to_f32(const uint16_t* src, float* dst, size_t n) { for (size_t i = 0; i < n; i++) dst[i] = (float)w2h(src[i]); }
+
+/* ------------------------------------------------ pointwise companions (fp32) ------------------ */
+/* Images are RGBA32F, pitches in floats; alpha is copied through (the reference functions take RGB).
+ * aux images (grain, dither) tile with wrap addressing: texel (x mod aw, y mod ah). */
+void fsr1o_lfga_f32(const float* in, size_t inPitch, const float* grain, int gw, int gh, size_t gPitch, float* out,
+                    size_t outPitch, int W, int H, float amount) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const float* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      const float* t = grain + (size_t)(y % gh) * gPitch + (size_t)(x % gw) * 4;
+      float* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      for (int k = 0; k < 3; k++) o[k] = c[k] + (t[k] * amount) * fminf(1.0f - c[k], c[k]);
+      o[3] = c[3];
+    }
+}
+
+void fsr1o_srtm_f32(const float* in, size_t inPitch, float* out, size_t outPitch, int W, int H, int inverse) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const float* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      float* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      const float m = fmaxf(c[0], fmaxf(c[1], c[2]));
+      const float r = inverse ? 1.0f / fmaxf((float)(1.0 / 32768.0), 1.0f - m) : 1.0f / (m + 1.0f);
+      for (int k = 0; k < 3; k++) o[k] = c[k] * r;
+      o[3] = c[3];
+    }
+}
+
+float fsr1o_tepd_dit(uint32_t px, uint32_t py, uint32_t frame) {
+  float x = (float)(px + frame), y = (float)py;
+  const float a = (float)((1.0 + sqrt(5.0)) / 2.0), b = (float)(1.0 / 3.69);
+  x = x * a + (y * b);
+  return x - floorf(x);
+}
+
+static inline float gt_zero(float m) { return satf(m * u2f(0x7f800000u)); } /* 0*inf = NaN -> 0 */
+
+/* dither == NULL: FsrTepdDitF(position, frame); else the .w channel of the tiled dither image, saturated
+ * (sample/src/DX12/FSR_Tonemapping.hlsl:87).  bits = 8 or 10. */
+void fsr1o_tepd_f32(const float* in, size_t inPitch, const float* dither, int dw, int dh, size_t dPitch, float* out,
+                    size_t outPitch, int W, int H, int bits, uint32_t frame) {
+  const float q = bits == 8 ? 255.0f : 1023.0f, rq = bits == 8 ? (float)(1.0 / 255.0) : (float)(1.0 / 1023.0);
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const float* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      float* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      const float dit = dither ? satf(dither[(size_t)(y % dh) * dPitch + (size_t)(x % dw) * 4 + 3])
+                               : fsr1o_tepd_dit((uint32_t)x, (uint32_t)y, frame);
+      for (int k = 0; k < 3; k++) {
+        float n = sqrtf(c[k]);
+        n = floorf(n * q) * rq;
+        const float a = n * n;
+        float b = n + rq;
+        b = b * b;
+        const float r = (c[k] - b) * prx_med_rcp(a - b);
+        o[k] = satf(n + gt_zero(dit - r) * rq);
+      }
+      o[3] = c[3];
+    }
+}

@@ -94,6 +94,10 @@ AH4 FsrRcasLoadH(ASW2 p) {
   return AH4(h_from_bits(t[0]), h_from_bits(t[1]), h_from_bits(t[2]), h_from_bits(t[3]));
 }
 void FsrRcasInputH(AH1& r, AH1& g, AH1& b) {}
+// the packed calling convention (ffx-fsr/ffx_fsr1.h:874-984): same loads, two pixels (ip, ip+(8,0)) per call
+#define FSR_RCAS_HX2 1
+AH4 FsrRcasLoadHx2(ASW2 p) { return FsrRcasLoadH(p); }
+void FsrRcasInputHx2(AH2& r, AH2& g, AH2& b) {}
 #endif
 
 #include "ffx_fsr1.h"  // rewritten copy
@@ -130,6 +134,36 @@ void fsr1ref_easu_f(const float* in, int inW, int inH, size_t inPitch, float* ou
       float* o = out + (size_t)y * outPitch + (size_t)x * 4;
       o[0] = pix.r; o[1] = pix.g; o[2] = pix.b; o[3] = 1.0f;
     }
+  }
+}
+
+
+// ---- the pointwise companions of the scaling path, fp32 ------------------------------------------------
+//   FsrLfgaF ffx-fsr/ffx_fsr1.h:1014   FsrSrtmF/FsrSrtmInvF :1044,1046   FsrTepdDitF :1086-1095   FsrTepdC8F/C10F :1100-1126
+// Pixels are n interleaved RGBA32F quadruples; alpha is not touched (the functions take AF3).
+void fsr1ref_lfga_f(float* c, const float* t, size_t n, float amount) {
+  for (size_t i = 0; i < n; i++) {
+    AF3 v(c[4 * i], c[4 * i + 1], c[4 * i + 2]);
+    FsrLfgaF(v, AF3(t[4 * i], t[4 * i + 1], t[4 * i + 2]), amount);
+    c[4 * i] = v.r; c[4 * i + 1] = v.g; c[4 * i + 2] = v.b;
+  }
+}
+void fsr1ref_srtm_f(float* c, size_t n, int inverse) {
+  for (size_t i = 0; i < n; i++) {
+    AF3 v(c[4 * i], c[4 * i + 1], c[4 * i + 2]);
+    if (inverse) FsrSrtmInvF(v); else FsrSrtmF(v);
+    c[4 * i] = v.r; c[4 * i + 1] = v.g; c[4 * i + 2] = v.b;
+  }
+}
+void fsr1ref_tepd_dit_f(float* dit, int w, int h, uint32_t frame) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) dit[(size_t)y * w + x] = FsrTepdDitF(AU2((uint)x, (uint)y), (AU1)frame);
+}
+void fsr1ref_tepd_f(float* c, const float* dit, size_t n, int bits) {
+  for (size_t i = 0; i < n; i++) {
+    AF3 v(c[4 * i], c[4 * i + 1], c[4 * i + 2]);
+    if (bits == 8) FsrTepdC8F(v, dit[i]); else FsrTepdC10F(v, dit[i]);
+    c[4 * i] = v.r; c[4 * i + 1] = v.g; c[4 * i + 2] = v.b;
   }
 }
 
@@ -193,6 +227,30 @@ void REF_NAME(fsr1ref_rcas_h)(const uint16_t* in, int W, int H, size_t inPitch, 
   }
 }
 #ifdef REF_BASE
+// FsrRcasHx2 (ffx-fsr/ffx_fsr1.h:888-984): lane i of a 16x1 strip produces pixels x0+i and x0+i+8.
+void fsr1ref_rcas_hx2(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+                      const uint32_t* con, int oob_clamp, int y0, int y1) {
+  AU4 c(con[0], con[1], con[2], con[3]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = y0; y < y1; y++) {
+    g_h = ImgH{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
+    for (int x0 = 0; x0 < W; x0 += 16)
+      for (int i = 0; i < 8; i++) {
+        AH2 pR, pG, pB;
+        FsrRcasHx2(pR, pG, pB, AU2((uint)(x0 + i), (uint)y), c);
+        AH4 q0, q1;
+        FsrRcasDepackHx2(q0, q1, pR, pG, pB);
+        if (x0 + i < W) {
+          uint16_t* o = out + (size_t)y * outPitch + (size_t)(x0 + i) * 4;
+          o[0] = h_to_bits(q0.r); o[1] = h_to_bits(q0.g); o[2] = h_to_bits(q0.b); o[3] = 0x3c00;
+        }
+        if (x0 + i + 8 < W) {
+          uint16_t* o = out + (size_t)y * outPitch + (size_t)(x0 + i + 8) * 4;
+          o[0] = h_to_bits(q1.r); o[1] = h_to_bits(q1.g); o[2] = h_to_bits(q1.b); o[3] = 0x3c00;
+        }
+      }
+  }
+}
 int fsr1ref_has_half(void) { return 1; }
 #endif
 #else

@@ -116,3 +116,69 @@ def rcas(img, con, clamp=False, y0=0, y1=None, lib=None, denoise=False, alpha=Fa
         suffix = {(False, False): "", (True, False): "_dn", (False, True): "_pa", (True, True): "_dnpa"}[(denoise, alpha)]
         getattr(lib, ("fsr1ref_rcas_h" if half else "fsr1ref_rcas_f") + suffix)(*args)
     return out.view(np.float16) if half else out
+
+
+def rcas_hx2(img, con, clamp=False):
+    """The reference's packed calling convention FsrRcasHx2 (two pixels per call), reference build only."""
+    lib = ref()
+    h, w = img.shape[:2]
+    src = img.view(np.uint16)
+    out = np.zeros((h, w, 4), np.uint16)
+    lib.fsr1ref_rcas_hx2(P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con),
+                         1 if clamp else 0, 0, h)
+    return out.view(np.float16)
+
+
+# ---- pointwise companions (LFGA / SRTM / TEPD), fp32 images [H,W,4] --------------------------------------------
+def lfga(img, grain, amount, lib=None):
+    h, w = img.shape[:2]
+    if lib is None or lib is oracle():
+        out = np.zeros_like(img)
+        oracle().fsr1o_lfga_f32(P(img.ctypes.data), Z(_pitch(img)), P(grain.ctypes.data), grain.shape[1], grain.shape[0],
+                                Z(_pitch(grain)), P(out.ctypes.data), Z(_pitch(out)), w, h, F(amount))
+        return out
+    out = np.ascontiguousarray(img).copy()
+    gy, gx = np.arange(h) % grain.shape[0], np.arange(w) % grain.shape[1]
+    tiled = np.ascontiguousarray(grain[gy][:, gx])
+    lib.fsr1ref_lfga_f(P(out.ctypes.data), P(tiled.ctypes.data), Z(h * w), F(amount))
+    return out
+
+
+def srtm(img, inverse=False, lib=None):
+    h, w = img.shape[:2]
+    if lib is None or lib is oracle():
+        out = np.zeros_like(img)
+        oracle().fsr1o_srtm_f32(P(img.ctypes.data), Z(_pitch(img)), P(out.ctypes.data), Z(_pitch(out)), w, h,
+                                1 if inverse else 0)
+        return out
+    out = np.ascontiguousarray(img).copy()
+    lib.fsr1ref_srtm_f(P(out.ctypes.data), Z(h * w), 1 if inverse else 0)
+    return out
+
+
+def tepd_dit(w, h, frame, lib=None):
+    if lib is None or lib is oracle():
+        oracle().fsr1o_tepd_dit.restype = ctypes.c_float
+        oracle().fsr1o_tepd_dit.argtypes = [U, U, U]
+        return np.array([[oracle().fsr1o_tepd_dit(x, y, frame) for x in range(w)] for y in range(h)], np.float32)
+    out = np.zeros((h, w), np.float32)
+    lib.fsr1ref_tepd_dit_f(P(out.ctypes.data), w, h, U(frame))
+    return out
+
+
+def tepd(img, bits, frame=0, dither=None, lib=None):
+    """dither: None -> FsrTepdDitF(position, frame); else a tiled [h,w,4] image whose .w channel is the dither."""
+    h, w = img.shape[:2]
+    if lib is None or lib is oracle():
+        out = np.zeros_like(img)
+        d = (P(dither.ctypes.data), dither.shape[1], dither.shape[0], Z(_pitch(dither))) if dither is not None else (P(0), 0, 0, Z(0))
+        oracle().fsr1o_tepd_f32(P(img.ctypes.data), Z(_pitch(img)), *d, P(out.ctypes.data), Z(_pitch(out)), w, h, bits, U(frame))
+        return out
+    out = np.ascontiguousarray(img).copy()
+    if dither is None:
+        dit = tepd_dit(w, h, frame, lib=lib)
+    else:
+        gy, gx = np.arange(h) % dither.shape[0], np.arange(w) % dither.shape[1]
+        dit = np.ascontiguousarray(np.clip(dither[gy][:, gx][..., 3], 0.0, 1.0).astype(np.float32))
+    lib.fsr1ref_tepd_f(P(out.ctypes.data), P(dit.ctypes.data), Z(h * w), bits)
+    return out

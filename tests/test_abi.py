@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export: " + n
     assert sorted(_lib.SYMBOLS) == names
-    assert L.fsr1_abi_version() == 1
+    assert L.fsr1_abi_version() == 2
 
 
 def test_error_strings_and_validation_without_gpu():
@@ -53,6 +53,21 @@ def test_error_strings_and_validation_without_gpu():
     a, b = ctypes.c_uint32(), ctypes.c_uint32()
     assert L.fsr1_easu_input_rows(econ, 64, 20, 40, ctypes.byref(a), ctypes.byref(b)) == 0
     assert (a.value, b.value) == (8, 21)  # rows floor((20+.5)/2-.5)-1 .. floor((39+.5)/2-.5)+2
+    # pointwise companions: same validation rules, all decided before any launch
+    h_img = _lib.Image(addr, 64, 8, 4, 0, 4, 1, 0)
+    u8_img = _lib.Image(addr, 32, 8, 4, 0, 4, 3, 0)
+    u10_img = _lib.Image(addr, 32, 8, 4, 0, 4, 4, 0)
+    other = _lib.Image(addr, 64, 8, 5, 0, 5, 1, 0)
+    assert L.fsr1_srtm(None, ctypes.byref(h_img), 0, 0, 0, None) == -1
+    assert L.fsr1_srtm(ctypes.byref(h_img), ctypes.byref(other), 0, 0, 0, None) == -1        # sizes differ
+    assert L.fsr1_srtm(ctypes.byref(h_img), ctypes.byref(u8_img), 0, 0, 0, None) == -2       # SRTM does not convert formats
+    assert L.fsr1_srtm(ctypes.byref(h_img), ctypes.byref(h_img), 1, 3, 2, None) == -1        # empty row range
+    assert L.fsr1_lfga(ctypes.byref(h_img), None, ctypes.byref(h_img), 0.5, 0, 0, None) == -1
+    assert L.fsr1_lfga(ctypes.byref(h_img), ctypes.byref(u8_img), ctypes.byref(h_img), 0.5, 0, 0, None) == -2  # grain is signed
+    assert L.fsr1_tepd(ctypes.byref(h_img), None, ctypes.byref(h_img), 9, 0, 0, 0, None) == -1   # bits must be 8 or 10
+    assert L.fsr1_tepd(ctypes.byref(h_img), None, ctypes.byref(u10_img), 8, 0, 0, 0, None) == -2  # 8-bit codes into RGB10A2
+    win = _lib.Image(addr, 64, 8, 64, 10, 4, 1, 0)
+    assert L.fsr1_srtm(ctypes.byref(win), ctypes.byref(win), 0, 0, 0, None) == -3            # window lacks rows [0,64)
     assert L.fsr1_launch_count() == 0
 
 
@@ -63,7 +78,7 @@ def test_cpp_filter_mirror_compiles_and_links(tmp_path):
     src.write_text('#include "fidelityfx-fsr_b200/fsr_filter.hpp"\n'
                    'int main(){ fsr1::FSR_Filter f; f.OnCreate(); fsr1::State s; s.renderWidth = 8;\n'
                    '  AU1 c[16]; FsrEasuCon(c, c+4, c+8, c+12, 8.f, 8.f, 8.f, 8.f, 16.f, 16.f);\n'
-                   '  return (fsr1_abi_version() == 1 && c[0] == 0x3f000000u) ? 0 : 1; }\n')
+                   '  return (fsr1_abi_version() == 2 && c[0] == 0x3f000000u) ? 0 : 1; }\n')
     exe = tmp_path / "f"
     libdir = os.path.join(ROOT, "fidelityfx-fsr_b200", "lib")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", ROOT, str(src), "-o", str(exe), "-L", libdir, "-lfsr1_b200",
