@@ -65,15 +65,16 @@ class FSR_Filter:
         """FSR_Filter::Upscale (FSR_Filter.cpp:101-141): constants, EASU dispatch, RCAS dispatch."""
         if pState.m_nUpscaleType != UPSCALE_TYPE_FSR_1_0:
             raise api.Fsr1Error("only the FSR 1.0 path is implemented (bilinear comparison mode is out of scope)")
-        if hdr:
-            raise api.Fsr1Error("the sample's HDR gamma-2 hook (Sample.x) is colour management, not FSR: out of scope")
+        # hdr: the sample's Sample.x == 1 (FSR_Filter.cpp:107,125: `hdr && !bUseRcas` for EASU, `hdr` for RCAS):
+        # the LAST pass squares its output (gamma 2.0 from TEPD back to linear)
+        flags = self.flags | (api.FLAG_OUTPUT_SQUARE if hdr else 0)
         if self._intermediary is None or self._display != (displayWidth, displayHeight):
             raise api.Fsr1Error("call OnCreateWindowSizeDependentResources for this display size first")
         econ = api.easu_con(pState.renderWidth, pState.renderHeight, pState.renderWidth, pState.renderHeight,
                             displayWidth, displayHeight)
         if pState.bUseRcas:
             rcon = api.rcas_con(pState.rcasAttenuation)
-            api.upscale(inputTexture, self._intermediary, outputTexture, econ, rcon, flags=self.flags, stream=stream)
+            api.upscale(inputTexture, self._intermediary, outputTexture, econ, rcon, flags=flags, stream=stream)
         else:
-            api.easu(inputTexture, outputTexture, econ, flags=self.flags, stream=stream)
+            api.easu(inputTexture, outputTexture, econ, flags=flags, stream=stream)
         return outputTexture

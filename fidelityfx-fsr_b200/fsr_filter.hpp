@@ -49,10 +49,12 @@ class FSR_Filter {
                const Texture& output, bool hdr = false) {
     if (!m_ctx || (uint32_t)displayWidth != m_displayWidth || (uint32_t)displayHeight != m_displayHeight)
       throw std::runtime_error("FSR_Filter: OnCreateWindowSizeDependentResources not called for this display size");
-    if (pState->m_nUpscaleType != 1 || hdr)
-      throw std::runtime_error("FSR_Filter: only the FSR 1.0 SDR path is implemented");
+    if (pState->m_nUpscaleType != 1)
+      throw std::runtime_error("FSR_Filter: only the FSR 1.0 path is implemented (no bilinear comparison mode)");
+    // hdr = the sample's Sample.x (FSR_Filter.cpp:107,125): the last pass squares its output
+    const uint32_t flags = (pState->bUseRcas ? 0u : FSR1_FLAG_NO_RCAS) | (hdr ? FSR1_FLAG_OUTPUT_SQUARE : 0u);
     check(fsr1_context_upscale(m_ctx, input.data, input.pitchBytes, output.data, output.pitchBytes,
-                               pState->rcasAttenuation, pState->bUseRcas ? 0u : FSR1_FLAG_NO_RCAS, stream));
+                               pState->rcasAttenuation, flags, stream));
   }
 
  private:

@@ -188,3 +188,23 @@ def test_sample_frame_chain_srtm_easu_rcas_inverse_lfga_tepd():
     u = code.cpu().numpy().view(np.uint32)
     codes = np.stack([u & 1023, (u >> 10) & 1023, (u >> 20) & 1023], axis=-1)
     assert np.array_equal(codes, _q(fin[..., :3], 10))
+
+
+def test_fsr_filter_hdr_flag_squares_the_last_pass():
+    """FSR_Filter::Upscale(..., hdr) (FSR_Filter.cpp:107,125): Sample.x = 1 on the pass that writes the output."""
+    iw, ih, ow, oh = 96, 54, 192, 108
+    src = torch.from_numpy(F.to_half(F.structured(iw, ih, 3))).cuda()
+    flt = F.FSR_Filter()
+    flt.OnCreate()
+    flt.OnCreateWindowSizeDependentResources(iw, ih, ow, oh)
+    for use_rcas in (True, False):
+        st = F.State(renderWidth=iw, renderHeight=ih, rcasAttenuation=0.25, bUseRcas=use_rcas)
+        plain = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+        hdr = torch.zeros_like(plain)
+        flt.Upscale(src, plain, ow, oh, st)
+        flt.Upscale(src, hdr, ow, oh, st, hdr=True)
+        torch.cuda.synchronize()
+        want = plain.float()
+        want[..., :3] = want[..., :3] * want[..., :3]
+        assert torch.equal(hdr, want.half())
+    flt.OnDestroy()
