@@ -62,6 +62,11 @@ int host_cell(uint32_t o, float scale, float offset) {
 
 float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
+// every flag include/fsr1_b200.h defines
+constexpr uint32_t kAllFlags = FSR1_FLAG_RCAS_CLAMP | FSR1_FLAG_EXACT | FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_NO_RCAS |
+                               FSR1_FLAG_H_REFERENCE | FSR1_FLAG_PRECISE | FSR1_FLAG_RCAS_DENOISE |
+                               FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE;
+
 bool window_holds(const fsr1_image* im, int first, int last) {  // logical rows [first,last]
   return first >= (int)im->row0 && last < (int)(im->row0 + im->rows);
 }
@@ -147,7 +152,7 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
               uint32_t flags, void* stream) {
   int rc;
   if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
-  if (!con) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!con || (flags & ~kAllFlags)) return FSR1_ERR_INVALID_ARGUMENT;
   if (in->format != out->format) return FSR1_ERR_UNSUPPORTED;
   if (y1 == 0) y1 = out->height;
   if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
@@ -186,7 +191,7 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
               uint32_t flags, void* stream) {
   int rc;
   if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
-  if (!con) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!con || (flags & ~kAllFlags)) return FSR1_ERR_INVALID_ARGUMENT;
   if (in->format != out->format) return FSR1_ERR_UNSUPPORTED;
   if (in->width != out->width || in->height != out->height) return FSR1_ERR_INVALID_ARGUMENT;
   if (y1 == 0) y1 = out->height;

@@ -15,6 +15,7 @@
 // EXACT policy: separate roundings, IEEE sqrt and division — the fp32 results are bit-identical to the reference
 // source compiled with -ffp-contract=off, for every storage format (fp16/unorm storage rounds that fp32 result once).
 // Alpha is carried through unchanged (the reference functions take RGB).
+#include <stdlib.h>
 #include "fsr1_common.cuh"
 
 namespace fsr1 {
@@ -119,34 +120,66 @@ __device__ __forceinline__ float4 apply_op(const PointParams& p, float4 c, int x
   }
 }
 
-template <typename SI, typename SO>
-__global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const PointParams p) {
-  const int x = blockIdx.x * kPointThreads + threadIdx.x;
-  const int yb = p.y0 + blockIdx.y * kRowsPerThread;
-  if (x >= p.out.w) return;
-  float4 c[kRowsPerThread];
+// kCols = false: a thread owns one column position and kRowsPerThread rows (CTA = 256 x 4 pixels);
+// kCols = true : a thread owns kRowsPerThread positions 256 apart in ONE row (CTA = 1024 x 1 pixels: one contiguous
+//               8-16 KB stretch of a row per CTA).  Same arithmetic, different DRAM access shape (FSR1_POINT_LAYOUT).
+template <typename SI, typename SO, bool kCols, int N>
+__global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const PointParams p, const int aux_step) {
+  int xs[N], ys[N];
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; r++)
-    if (yb + r < p.y1) c[r] = load4<SI>(p.in, x, yb + r);
+  for (int r = 0; r < N; r++) {
+    xs[r] = kCols ? blockIdx.x * (kPointThreads * N) + threadIdx.x + kPointThreads * r : blockIdx.x * kPointThreads + threadIdx.x;
+    ys[r] = kCols ? p.y0 + (int)blockIdx.y : p.y0 + (int)blockIdx.y * N + r;
+  }
+  float4 c[N];
+#pragma unroll
+  for (int r = 0; r < N; r++)
+    if (xs[r] < p.out.w && ys[r] < p.y1) c[r] = load4<SI>(p.in, xs[r], ys[r]);
+  // position inside the aux tile: one division per thread, then incremental with wrap
   int ax = 0, ay = 0;
   if (p.aux_format) {
-    ax = x % p.aux.w;
-    ay = yb % p.aux.h;
+    ax = xs[0] % p.aux.w;
+    ay = ys[0] % p.aux.h;
   }
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; r++)
-    if (yb + r < p.y1) {
-      const float4 o = apply_op(p, c[r], x, yb + r, ax, ay);
-      Px<SO>::store(p.out, x, yb + r, o.x, o.y, o.z, o.w);
-      if (++ay >= p.aux.h) ay = 0;
+  for (int r = 0; r < N; r++) {
+    if (xs[r] < p.out.w && ys[r] < p.y1) {
+      const float4 o = apply_op(p, c[r], xs[r], ys[r], ax, ay);
+      Px<SO>::store(p.out, xs[r], ys[r], o.x, o.y, o.z, o.w);
     }
+    if (kCols) {
+      ax += aux_step;  // aux_step = 256 mod aux width (host)
+      if (ax >= p.aux.w) ax -= p.aux.w;
+    } else if (++ay >= p.aux.h) {
+      ay = 0;
+    }
+  }
+}
+
+// development knobs: FSR1_POINT_LAYOUT = 0 (256 x N CTAs), 1 (256N x 1 CTAs); FSR1_POINT_N = 4 | 8 pixels per thread
+static int point_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <typename SI, typename SO, int N>
+static cudaError_t launch_n(const PointParams& p, cudaStream_t s, int layout) {
+  const int aux_step = p.aux_format ? kPointThreads % p.aux.w : 0;
+  if (layout == 1) {
+    const int per_cta = kPointThreads * N;
+    const dim3 grid((p.out.w + per_cta - 1) / per_cta, p.y1 - p.y0, 1);
+    pointwise_kernel<SI, SO, true, N><<<grid, kPointThreads, 0, s>>>(p, aux_step);
+  } else {
+    const dim3 grid((p.out.w + kPointThreads - 1) / kPointThreads, (p.y1 - p.y0 + N - 1) / N, 1);
+    pointwise_kernel<SI, SO, false, N><<<grid, kPointThreads, 0, s>>>(p, aux_step);
+  }
+  return cudaGetLastError();
 }
 
 template <typename SI, typename SO>
 static cudaError_t launch_one(const PointParams& p, cudaStream_t s) {
-  const dim3 grid((p.out.w + kPointThreads - 1) / kPointThreads, (p.y1 - p.y0 + kRowsPerThread - 1) / kRowsPerThread, 1);
-  pointwise_kernel<SI, SO><<<grid, kPointThreads, 0, s>>>(p);
-  return cudaGetLastError();
+  static const int layout = point_knob("FSR1_POINT_LAYOUT", 0), n = point_knob("FSR1_POINT_N", kRowsPerThread);
+  return n == 8 ? launch_n<SI, SO, 8>(p, s, layout) : launch_n<SI, SO, kRowsPerThread>(p, s, layout);
 }
 
 // in_format == out_format for every op; TEPD may also write its 8/10-bit code values straight into a UNORM image

@@ -43,6 +43,8 @@ def test_error_strings_and_validation_without_gpu():
     assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(bad_fmt), con, 0, 0, 0, None) == -1
     f32_out = _lib.Image(addr, 256, 16, 8, 0, 8, 2, 0)
     assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(f32_out), con, 0, 0, 0, None) == -2  # mixed formats
+    assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(ok_in), con, 0, 0, 1 << 20, None) == -1  # unknown flag
+    assert L.fsr1_rcas(ctypes.byref(ok_in), ctypes.byref(ok_in), con, 0, 0, 1 << 20, None) == -1
     small_pitch = _lib.Image(addr, 32, 8, 4, 0, 4, 1, 0)
     assert L.fsr1_easu(ctypes.byref(small_pitch), ctypes.byref(ok_in), con, 0, 0, 0, None) == -1
     # window that does not hold the rows EASU would read -> FSR1_ERR_WINDOW, before any launch

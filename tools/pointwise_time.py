@@ -24,7 +24,9 @@ def timeit(fn, n=100):
 
 rows = []
 grain16 = (torch.rand((128, 128, 4), device="cuda") - 0.5).half()
-for dt, bpp in ((torch.float16, 8), (torch.float32, 16)):
+HALF_ONLY = "--half-only" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--half-only"]
+for dt, bpp in (((torch.float16, 8),) if HALF_ONLY else ((torch.float16, 8), (torch.float32, 16))):
     ins = [torch.rand((H, W, 4), device="cuda").to(dt) for _ in range(R)]
     outs = [torch.empty_like(ins[0]) for _ in range(R)]
     grain = grain16.to(dt)
