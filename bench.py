@@ -350,9 +350,10 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["GBps"], "peak": peak,
                     "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom], "us_per_launch": kernels[dom]["us"],
-                    "note": "EASU is FMA-pipe-bound on B200, not HBM-bound: ~200 multiply-add-class ops per output pixel and "
-                            "HFMA2 issues at half the FFMA rate, i.e. >= 44 us per 4K frame at 100% pipe utilisation vs 12.6 us at "
-                            "the HBM roofline (ncu: profiles/r01_ncu_summary.txt, DESIGN.md section 4)"}
+                    "note": "EASU is instruction-issue-bound on B200, not HBM-bound: 182 instructions per output pixel at the "
+                            "2.1-2.6 inst/cycle/SM this mix can issue (HFMA2, FFMA2 and scalar FFMA all sustain ~2 inst/cycle/SM: "
+                            "profiles/r01_ubench_pipes.txt) is >= 58 us per 4K frame vs 12.6 us at the HBM roofline; the kernel "
+                            "runs at 2.53 inst/cycle/SM (ncu: profiles/r01_ncu_summary.txt, DESIGN.md section 4)"}
         path_bytes = alg["easu"] + alg["rcas"]
         kernels["path"] = {"algorithmic_bytes": path_bytes, "us": ms / K * 1e3,
                            "GBps": path_bytes / (ms / K * 1e-3) / 1e9, "frac_of_hbm_peak": path_bytes / (ms / K * 1e-3) / 1e9 / peak}

@@ -16,8 +16,9 @@
 // Precision split (DESIGN.md "numerics"): everything that decides the filter's ORIENTATION is fp32 — in
 // half it is ill-conditioned where gradients nearly cancel and differs from the fp32 algorithm by up to
 // 0.1; the taps (the bulk of the arithmetic) are half2 and stay within ~5e-3 of the fp32 oracle.
-// Pipe split: on B200 HFMA2 issues at half the FFMA rate (one 16-lane sub-pipe), so a kernel that is all
-// half2 is bound by that pipe; keeping the per-pixel set-up in fp32 balances the two FMA sub-pipes.
+// Issue model (tools/ubench_pipes.cu, profiles/r01_ubench_pipes.txt): on B200 HFMA2, FFMA2 and scalar FFMA all
+// sustain ~2 warp-instructions per cycle per SM and mixed streams 2.1-2.6, so half2 buys registers and shared-memory
+// bytes, not issue slots; this kernel runs at 2.53 inst/cycle/SM, i.e. instruction count is what is left to cut.
 //
 // Tap weights use the expanded quadratic form of the rotated, anisotropically scaled distance
 //   d2(ox,oy) = qa*ox^2 + qb*ox*oy + qc*oy^2,  qa = l2x^2 dx^2 + l2y^2 dy^2,  qc = l2x^2 dy^2 + l2y^2 dx^2,
