@@ -64,6 +64,25 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
   return __hmul2(wb, wa);
 }
 
+// experimental (FSR1_EASU_QUAD_VARIANT=8, unmeasured): the clamp as a packed 16-bit INTEGER min (VIMNMX.S16x2, integer
+// ALU pipe — HMNMX2 does not overlap with HFMA2 in the microbenchmark, integer ops do).  clp > 0, so comparing the bit
+// patterns as signed 16-bit integers orders every non-negative d2 correctly and returns d2 itself when rounding made
+// it slightly negative: identical results to __hmin2 for finite inputs.
+__device__ __forceinline__ __half2 tap_weight_iclamp(__half2 d2, __half2 lob, __half2 clp) {
+  uint32_t r;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(h22u(d2)), "r"(h22u(clp)));
+  d2 = u2h2(r);
+  const __half2 wb = __hfma2(__hfma2(h2c(0.25f), d2, h2c(-1.25f)), d2, h2c(1.0f));
+  __half2 wa = __hfma2(lob, d2, h2c(-1.0f));
+  wa = __hmul2(wa, wa);
+  return __hmul2(wb, wa);
+}
+
+template <int kTap> __device__ __forceinline__ __half2 tap_weight_sel(__half2 d2, __half2 lob, __half2 clp) {
+  if constexpr (kTap == 3) return tap_weight_iclamp(d2, lob, clp);
+  else return tap_weight(d2, lob, clp);
+}
+
 // the same without the distance clamp, for taps that provably never reach it (see quad_pair<.., 1>)
 __device__ __forceinline__ __half2 tap_weight_unclamped(__half2 d2, __half2 lob) {
   const __half2 wb = __hfma2(__hfma2(h2c(0.25f), d2, h2c(-1.25f)), d2, h2c(1.0f));
@@ -327,7 +346,7 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
     const __half2 d2 = __hfma2(qa, __floats2half2_rn(oxA * oxA, oxB * oxB),                                  \
                                __hfma2(qc, __floats2half2_rn(oy * oy, oy * oy),                              \
                                        __hmul2(qb, __floats2half2_rn(oxA * oy, oxB * oy))));                 \
-    const __half2 w = tap_weight(d2, lob, clp);                                                             \
+    const __half2 w = tap_weight_sel<kTap>(d2, lob, clp);                                                   \
     const __half2 rg = u2h2(t[R][K].x), ba = u2h2(t[R][K].y);                                               \
     aR = __hfma2(__low2half2(rg), w, aR);                                                                   \
     aG = __hfma2(__high2half2(rg), w, aG);                                                                  \
@@ -339,7 +358,7 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
     constexpr float oxA = (float)((K)-1) - 0.25f, oxB = (float)((K)-1) - 0.75f;                               \
     const __half2 ox = __floats2half2_rn(oxA, oxB);                                                         \
     const __half2 d2 = __hfma2(__hfma2(qa, ox, rowB##R), ox, rowC##R);                                       \
-    const __half2 w = (INNER) ? tap_weight_unclamped(d2, lob) : tap_weight(d2, lob, clp);                   \
+    const __half2 w = (INNER) ? tap_weight_unclamped(d2, lob) : tap_weight_sel<kTap>(d2, lob, clp);                   \
     const __half2 rg = u2h2(t[R][K].x), ba = u2h2(t[R][K].y);                                               \
     aR = __hfma2(__low2half2(rg), w, aR);                                                                   \
     aG = __hfma2(__high2half2(rg), w, aG);                                                                  \
@@ -371,6 +390,38 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
   outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
 }
 
+// ---- experimental (FSR1_EASU_QUAD_VARIANT=7, not yet measured): the per-pixel fp32 analysis of a pixel PAIR in
+// packed f32x2 (FFMA2 / FMUL2 / FADD2 issue at the scalar FFMA rate on B200, profiles/r01_ubench_pipes.txt, so this
+// halves the fp32 FMA-class instructions of phase 3).  Lane .x = pixel A, .y = pixel B; the operations per lane are
+// exactly those of pixel_shape().
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+struct Shape2 { float2 qa, qb, qc, lob, clp; };
+__device__ __forceinline__ Shape2 pixel_shape2(float2 dx, float2 dy, float2 len) {
+  const float2 dirR = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+  const bool zx = dirR.x < (1.0f / 32768.0f), zy = dirR.y < (1.0f / 32768.0f);
+  const float2 rs = mk2(zx ? 1.0f : prx_lo_rsq(dirR.x), zy ? 1.0f : prx_lo_rsq(dirR.y));
+  dx = __fmul2_rn(mk2(zx ? 1.0f : dx.x, zy ? 1.0f : dx.y), rs);
+  dy = __fmul2_rn(dy, rs);
+  len = __fmul2_rn(len, bc2(0.5f));
+  len = __fmul2_rn(len, len);
+  const float2 dx2 = __fmul2_rn(dx, dx), dy2 = __fmul2_rn(dy, dy);
+  const float2 rmax = mk2(prx_lo_rcp(fmaxf(fabsf(dx.x), fabsf(dy.x))), prx_lo_rcp(fmaxf(fabsf(dx.y), fabsf(dy.y))));
+  const float2 stretch = __fmul2_rn(__fadd2_rn(dx2, dy2), rmax);
+  const float2 l2x = __ffma2_rn(__fadd2_rn(stretch, bc2(-1.0f)), len, bc2(1.0f));
+  const float2 l2y = __ffma2_rn(bc2(-0.5f), len, bc2(1.0f));
+  Shape2 s;
+  s.lob = __ffma2_rn(bc2((float)((1.0 / 4.0 - 0.04) - 0.5)), len, bc2(0.5f));
+  s.clp = mk2(prx_lo_rcp(s.lob.x), prx_lo_rcp(s.lob.y));
+  const float2 X2 = __fmul2_rn(l2x, l2x), Y2 = __fmul2_rn(l2y, l2y);
+  s.qa = __ffma2_rn(X2, dx2, __fmul2_rn(Y2, dy2));
+  s.qc = __ffma2_rn(X2, dy2, __fmul2_rn(Y2, dx2));
+  s.qb = __fmul2_rn(__fmul2_rn(__fmul2_rn(dx, dy), bc2(2.0f)), __ffma2_rn(Y2, bc2(-1.0f), X2));
+  return s;
+}
+__device__ __forceinline__ Shape lane_x(const Shape2& s) { return Shape{s.qa.x, s.qb.x, s.qc.x, s.lob.x, s.clp.x}; }
+__device__ __forceinline__ Shape lane_y(const Shape2& s) { return Shape{s.qa.y, s.qb.y, s.qc.y, s.lob.y, s.clp.y}; }
+
 // Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
 // k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
 template <int kTap = 0>
@@ -396,6 +447,35 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
     const __half2 mxBA = __hmax2(__hmax2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmax2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
     const __half2 mnR = __low2half2(mnRG), mnG = __high2half2(mnRG), mnB = __low2half2(mnBA);
     const __half2 mxR = __low2half2(mxRG), mxG = __high2half2(mxRG), mxB = __low2half2(mxBA);
+    if constexpr (kTap >= 2) {
+      constexpr int kPairTap = kTap == 2 ? 1 : 3;
+      // packed pair (A: px=.25, B: px=.75): T = top texel row f,g blended horizontally, Bm = bottom texel row j,k
+      const float2 wF = mk2(0.75f, 0.25f), wG = mk2(0.25f, 0.75f);
+      const float2 Tx = __ffma2_rn(bc2(g.x), wG, __fmul2_rn(bc2(f.x), wF)), Ty = __ffma2_rn(bc2(g.y), wG, __fmul2_rn(bc2(f.y), wF));
+      const float2 Tz = __ffma2_rn(bc2(g.z), wG, __fmul2_rn(bc2(f.z), wF));
+      const float2 Bx = __ffma2_rn(bc2(k.x), wG, __fmul2_rn(bc2(j.x), wF)), By = __ffma2_rn(bc2(k.y), wG, __fmul2_rn(bc2(j.y), wF));
+      const float2 Bz = __ffma2_rn(bc2(k.z), wG, __fmul2_rn(bc2(j.z), wF));
+      unsigned char* orow2 = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
+      const bool okA2 = oxA >= 0, okB2 = oxA + 1 < p.out.w;
+      uint2 oA2, oB2;
+      if (rowT) {
+        const Shape2 s2 = pixel_shape2(__ffma2_rn(Bx, bc2(0.25f), __fmul2_rn(Tx, bc2(0.75f))),
+                                       __ffma2_rn(By, bc2(0.25f), __fmul2_rn(Ty, bc2(0.75f))),
+                                       __ffma2_rn(Bz, bc2(0.25f), __fmul2_rn(Tz, bc2(0.75f))));
+        quad_pair<false, kPairTap>(tp, lane_x(s2), lane_y(s2), mnR, mnG, mnB, mxR, mxG, mxB, oA2, oB2);
+        if (okA2) *reinterpret_cast<uint2*>(orow2) = oA2;
+        if (okB2) *reinterpret_cast<uint2*>(orow2 + 8) = oB2;
+      }
+      if (rowB) {
+        const Shape2 s2 = pixel_shape2(__ffma2_rn(Bx, bc2(0.75f), __fmul2_rn(Tx, bc2(0.25f))),
+                                       __ffma2_rn(By, bc2(0.75f), __fmul2_rn(Ty, bc2(0.25f))),
+                                       __ffma2_rn(Bz, bc2(0.75f), __fmul2_rn(Tz, bc2(0.25f))));
+        quad_pair<true, kPairTap>(tp, lane_x(s2), lane_y(s2), mnR, mnG, mnB, mxR, mxG, mxB, oA2, oB2);
+        if (okA2) *reinterpret_cast<uint2*>(orow2 + p.out.pitch) = oA2;
+        if (okB2) *reinterpret_cast<uint2*>(orow2 + p.out.pitch + 8) = oB2;
+      }
+      return;
+    }
     // bilinear blends with the four constant weight sets (pp = .25/.75): horizontal first
     const float fx = 0.75f, gx = 0.25f;
     const float3 t25 = make_float3(fmaf(g.x, gx, f.x * fx), fmaf(g.y, gx, f.y * fx), fmaf(g.z, gx, f.z * fx));
@@ -408,14 +488,14 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
     if (rowT) {
       const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
       const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
-      quad_pair<false, kTap>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<false, (kTap >= 2 ? 1 : kTap)>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
     }
     if (rowB) {
       const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
       const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
-      quad_pair<true, kTap>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<true, (kTap >= 2 ? 1 : kTap)>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
     }
@@ -615,7 +695,8 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
 
   if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
     // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
-    // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance)
+    // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance),
+    // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp)
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("FSR1_EASU_QUAD_VARIANT"); variant = e ? atoi(e) : 6; }
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
@@ -646,6 +727,8 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     }
     if (variant == 5) return launch(easu_h_quad2x_kernel<4, 7>, 4, 7, "easu_h_quad2x<4w,7/sm,tma2>");
     if (variant == 2) return launch(easu_h_quad2x_kernel<4, 6, 0>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,plain>");
+    if (variant == 7) return launch(easu_h_quad2x_kernel<4, 6, 2>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape>");  // experimental
+    if (variant == 8) return launch(easu_h_quad2x_kernel<4, 6, 3>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp>");  // experimental
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6, 1>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");

@@ -32,6 +32,7 @@ constexpr int kIters = 2000;
 #define IADD(i)  asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
 #define LOP(i)   asm volatile("prmt.b32 %0, %0, %1, 0x5432;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
 #define FMNMX(i) asm volatile("min.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(f[(i + 1) & 7]));
+#define IMIN16(i) asm volatile("min.s16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
 #define LDS(i)   asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(u[i]) : "r"(saddr + 4 * i));
 #define MUFU(i)  asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
 
@@ -90,6 +91,13 @@ KERNEL(k_ffma_lop, REP8(MIX(FFMA3, LOP)), 128)
 KERNEL(k_hfma_ffma2, REP8(MIX(HFMA3, FFMA2)), 128)
 KERNEL(k_ffma_ffma2, REP8(MIX(FFMA3, FFMA2)), 128)
 KERNEL(k_hfmai_ffmai, REP8(MIX(HFMAI, FFMAI)), 128)
+KERNEL(k_imin16, REP8(CHAINS8(IMIN16)), 64)
+KERNEL(k_hfma_imin16, REP8(MIX(HFMA3, IMIN16)), 128)
+KERNEL(k_hfma_prmt, REP8(MIX(HFMA3, LOP)), 128)
+KERNEL(k_ffma2_prmt, REP8(MIX(FFMA2, LOP)), 128)
+KERNEL(k_ffma2_hmin, REP8(MIX(FFMA2, HMIN)), 128)
+#define TAPMIX2 HFMA3(0) HFMA3(1) HFMA3(2) IMIN16(3) HFMA3(4) HFMA3(5) HFMA3(6) FFMA2(7)
+KERNEL(k_tapmix2, REP8(TAPMIX2 TAPMIX2), 128)
 
 typedef void (*kern_t)(unsigned long long*, float, float, uint32_t, uint32_t, uint32_t, unsigned long long,
                        unsigned long long);
@@ -126,13 +134,26 @@ int main() {
       {"HFMA2 + FFMA2 1:1", k_hfma_ffma2, 128, "alternating"},
       {"FFMA + FFMA2 1:1", k_ffma_ffma2, 128, "alternating"},
       {"HFMA2 imm + FFMA imm 1:1", k_hfmai_ffmai, 128, "alternating"},
+      {"VIMNMX.S16x2", k_imin16, 64, "min.s16x2 (packed integer min)"},
+      {"HFMA2 + VIMNMX.S16x2 1:1", k_hfma_imin16, 128, "alternating"},
+      {"HFMA2 + PRMT 1:1", k_hfma_prmt, 128, "alternating"},
+      {"FFMA2 + PRMT 1:1", k_ffma2_prmt, 128, "alternating"},
+      {"FFMA2 + HMNMX2 1:1", k_ffma2_hmin, 128, "alternating"},
+      {"tap mix, int clamp, FFMA2", k_tapmix2, 128, "8 x (6 HFMA2, 1 VIMNMX.S16x2, 1 FFMA2)"},
   };
-  printf("device SMs: %d; warp-instructions per clock per SM (4.00 = one per SMSP per clock)\n", sms);
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+  printf("device SMs: %d; warp-instructions per clock64 tick per SM; nominal SM clock %.0f MHz\n", sms, khz / 1e3);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
   for (auto& t : tests) {
     double best = 0;
     for (int rep = 0; rep < 3; rep++) {
       cudaMemset(out, 0, 16 + 8 * 4096);
+      cudaEventRecord(e0);
       t.k<<<sms * 2, 256>>>(out, 1.0001f, 0.5f, 0x3c003c01u, 0x38003801u, 3u, 0x3f8000013f800002ull, 0x3f0000003f000001ull);
+      cudaEventRecord(e1);
       cudaMemcpy(host, out, 16 + 8 * (size_t)(sms * 2), cudaMemcpyDeviceToHost);
       const unsigned long long cyc = host[0];
       int ctas = 0;  // CTAs resident on the SM whose CTA 0 was timed (the block scheduler does not deal exactly 2 per SM)
@@ -140,7 +161,12 @@ int main() {
       if (cudaGetLastError() != cudaSuccess || cyc == 0) { printf("%-26s FAILED\n", t.name); break; }
       const double rate = 8.0 * ctas * (double)t.per_iter * kIters / (double)cyc;
       if (rate > best) best = rate;
-      if (rep == 0 && &t == &tests[0]) printf("CTAs resident on the timed SM: %d (%d warps)\n", ctas, 8 * ctas);
+      if (rep == 2 && &t == &tests[0]) {  // calibrate the tick against wall clock (kernel time ~ timed loop, launch overhead small at 0.3+ ms)
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("CTAs resident on the timed SM: %d (%d warps); clock64 advanced %.0f ticks in a %.3f ms kernel => <= %.0f MHz tick rate\n",
+               ctas, 8 * ctas, (double)cyc, ms, (double)cyc / (ms * 1e3));
+      }
     }
     printf("%-26s %5.2f inst/clk/SM   (%s)\n", t.name, best, t.what);
   }
