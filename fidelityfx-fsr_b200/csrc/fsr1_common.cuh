@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace fsr1 {
 
@@ -142,6 +143,14 @@ template <> struct Px<Unorm10> {
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// Development knobs: integer environment variables read once per process (thread-safe through a function-local static
+// at each use site).  They select measured-and-rejected or not-yet-measured kernel variants; the defaults are the
+// production configuration and nothing in the public API depends on them.
+static inline int env_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // launchers (defined in the .cu files, called from fsr1_capi.cu)
 cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name);

@@ -697,13 +697,12 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
     // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance),
     // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp)
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("FSR1_EASU_QUAD_VARIANT"); variant = e ? atoi(e) : 6; }
+    static const int variant = env_knob("FSR1_EASU_QUAD_VARIANT", 6);
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
     const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
-    static int cap = -1;  // FSR1_EASU_CTAS_PER_SM: leave room on every SM for a concurrently running kernel (frame pipelining)
-    if (cap < 0) { const char* e = getenv("FSR1_EASU_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }
+    // FSR1_EASU_CTAS_PER_SM: leave room on every SM for a concurrently running kernel (measured: slower, with and without pipelining)
+    static const int cap = env_knob("FSR1_EASU_CTAS_PER_SM", 0);
     auto launch = [&](auto kernel, int nw, int per_sm, const char* nm) -> cudaError_t {
       const int cy = 2 * nw;
       if (cap > 0 && cap < per_sm) per_sm = cap;

@@ -158,11 +158,6 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const PointPar
 
 // development knobs: FSR1_POINT_LAYOUT = 0 (256 x N CTAs), 1 = default (256N x 1 CTAs: 8 % faster on RGBA16F, one
 // contiguous stretch of a row per CTA); FSR1_POINT_N = 4 (default) | 8 pixels per thread (slower: registers)
-static int point_knob(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 template <typename SI, typename SO, int N>
 static cudaError_t launch_n(const PointParams& p, cudaStream_t s, int layout) {
   const int aux_step = p.aux_format ? kPointThreads % p.aux.w : 0;
@@ -179,7 +174,7 @@ static cudaError_t launch_n(const PointParams& p, cudaStream_t s, int layout) {
 
 template <typename SI, typename SO>
 static cudaError_t launch_one(const PointParams& p, cudaStream_t s) {
-  static const int layout = point_knob("FSR1_POINT_LAYOUT", 1), n = point_knob("FSR1_POINT_N", kRowsPerThread);
+  static const int layout = env_knob("FSR1_POINT_LAYOUT", 1), n = env_knob("FSR1_POINT_N", kRowsPerThread);
   return n == 8 ? launch_n<SI, SO, 8>(p, s, layout) : launch_n<SI, SO, kRowsPerThread>(p, s, layout);
 }
 

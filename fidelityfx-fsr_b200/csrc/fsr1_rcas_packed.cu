@@ -164,8 +164,7 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
   // development knob: FSR1_RCAS_VARIANT = 0 (8-warp CTAs, 4 rows/lane, MUFU), 1 (4 rows, Newton), 2 (8 rows/lane, MUFU),
   // 3 = default (as 0 with 4-warp CTAs: same kernel time, but the smaller CTA starts earlier in the tail of the
   // preceding EASU and shares SMs with it when frames are pipelined: 92.1 -> 90.7 us per frame back to back)
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("FSR1_RCAS_VARIANT"); variant = e ? atoi(e) : 3; }
+  static const int variant = env_knob("FSR1_RCAS_VARIANT", 3);
   const int rows_per_cta = (variant == 3 ? 4 : kWarps) * (variant == 2 ? 8 : 4);
   const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + rows_per_cta - 1) / rows_per_cta, 1);
   if (variant == 3) {
