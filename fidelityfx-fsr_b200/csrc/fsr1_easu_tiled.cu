@@ -424,13 +424,15 @@ __device__ __forceinline__ Shape lane_y(const Shape2& s) { return Shape{s.qa.y, 
 
 // Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
 // k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
-template <int kTap = 0>
+// kFast (experimental, FSR1_EASU_QUAD_VARIANT=9): the tile lies strictly inside the image and the row range, so every
+// bounds predicate is true and is dropped at compile time.
+template <int kTap = 0, bool kFast = false>
 __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __restrict__ tile, const float4* __restrict__ S,
                                           int gx0, int gy0, int lane, int r) {
   const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
     const int oyT = (gy0 + 1 + r) * 2 + 1;     // output rows 2m+1 (top pair), 2m+2 (bottom pair)
-    const bool rowT = oyT >= p.y0 && oyT < p.y1, rowB = oyT + 1 >= p.y0 && oyT + 1 < p.y1;
-    if (oxA >= p.out.w || !(rowT || rowB)) return;
+    const bool rowT = kFast || (oyT >= p.y0 && oyT < p.y1), rowB = kFast || (oyT + 1 >= p.y0 && oyT + 1 < p.y1);
+    if (!kFast && (oxA >= p.out.w || !(rowT || rowB))) return;
     uint2 tp[4][4];
     const uint2* t0 = tile + r * kQBW + lane;
 #pragma unroll
@@ -456,7 +458,7 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
       const float2 Bx = __ffma2_rn(bc2(k.x), wG, __fmul2_rn(bc2(j.x), wF)), By = __ffma2_rn(bc2(k.y), wG, __fmul2_rn(bc2(j.y), wF));
       const float2 Bz = __ffma2_rn(bc2(k.z), wG, __fmul2_rn(bc2(j.z), wF));
       unsigned char* orow2 = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
-      const bool okA2 = oxA >= 0, okB2 = oxA + 1 < p.out.w;
+      const bool okA2 = kFast || oxA >= 0, okB2 = kFast || oxA + 1 < p.out.w;
       uint2 oA2, oB2;
       if (rowT) {
         const Shape2 s2 = pixel_shape2(__ffma2_rn(Bx, bc2(0.25f), __fmul2_rn(Tx, bc2(0.75f))),
@@ -508,7 +510,7 @@ template <int NW> struct __align__(128) QuadSmem {
   uint64_t bar[2];
 };
 
-template <int NW, int MINB, int kTap = 0>
+template <int NW, int MINB, int kTap = 0, bool kFastPath = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x,
                      const int n_tiles, const int mbase) {
@@ -561,8 +563,21 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     }
     __syncthreads();
 
+    if constexpr (kFastPath) {
+      // every output pixel of the tile (columns 2(gx0+1)+1 .. 2(gx0+32)+2, rows 2(gy0+1)+1 .. 2(gy0+2NW)+2) is in range
+      const bool inside = 2 * (gx0 + 1) + 1 >= 0 && 2 * (gx0 + 32) + 2 < p.out.w && 2 * (gy0 + 1) + 1 >= p.y0 &&
+                          2 * (gy0 + C::kCY) + 2 < p.y1;
+      if (inside) {
 #pragma unroll 1
-    for (int q = 0; q < 2; q++) quad_cell<kTap>(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+        for (int q = 0; q < 2; q++) quad_cell<kTap, true>(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) quad_cell<kTap, false>(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) quad_cell<kTap>(p, tile, sm.S, gx0, gy0, lane, warp + q * NW);
+    }
     __syncthreads();  // L, S and this tile buffer are free again
   }
 }
@@ -696,7 +711,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
     // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
     // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance),
-    // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp)
+    // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp), 9 (8 + predicate-free path for interior tiles)
     static const int variant = env_knob("FSR1_EASU_QUAD_VARIANT", 6);
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
@@ -728,6 +743,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     if (variant == 2) return launch(easu_h_quad2x_kernel<4, 6, 0>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,plain>");
     if (variant == 7) return launch(easu_h_quad2x_kernel<4, 6, 2>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape>");  // experimental
     if (variant == 8) return launch(easu_h_quad2x_kernel<4, 6, 3>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp>");  // experimental
+    if (variant == 9) return launch(easu_h_quad2x_kernel<4, 6, 3, true>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp,interior>");  // experimental
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6, 1>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");
