@@ -208,3 +208,40 @@ def test_fsr_filter_hdr_flag_squares_the_last_pass():
         want[..., :3] = want[..., :3] * want[..., :3]
         assert torch.equal(hdr, want.half())
     flt.OnDestroy()
+
+
+def _golden_runners_gpu():
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def srtm(img, inverse):
+        return _run(lambda a, b: api.srtm(a, b, inverse=inverse), img)
+
+    def lfga(img, grain, amount):
+        g = up(grain)
+        return _run(lambda a, b: api.lfga(a, g, b, amount), img)
+
+    def tepd(img, bits, frame, dither):
+        d = up(dither) if dither is not None else None
+        return _run(lambda a, b: api.tepd(a, b, bits, frame=frame, dither=d), img)
+
+    return srtm, lfga, tepd
+
+
+def check_against_pointwise_golden(srtm, lfga, tepd):
+    """Shared by the GPU test below and by tests/test_oracle.py-style CPU use: every committed array, bit for bit."""
+    import os
+    P = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fsr1_pointwise_golden.npz"))
+    sdr, hdr, grain, noise = P["sdr"], P["hdr"], P["grain"], P["noise"]
+    assert np.array_equal(_bits(srtm(hdr, False)), _bits(P["srtm"]))
+    assert np.array_equal(_bits(srtm(P["srtm"], True)), _bits(P["srtm_inv"]))
+    for amount in (0.0, 0.35, 1.0):
+        assert np.array_equal(_bits(lfga(sdr, grain, amount)), _bits(P["lfga_%g" % amount])), amount
+    for b in (8, 10):
+        assert np.array_equal(_bits(tepd(sdr, b, 5, None)), _bits(P["tepd%d_f5" % b])), b
+        assert np.array_equal(_bits(tepd(sdr, b, 0, noise)), _bits(P["tepd%d_noise" % b])), b
+
+
+def test_pointwise_against_committed_golden_vectors():
+    """The reference's own outputs (tests/golden/make_pointwise_golden.py), 300 px wide with 12x5 / 9x7 aux tiles: more
+    than one pixel per thread in a row and a tile width that does not divide the thread stride."""
+    check_against_pointwise_golden(*_golden_runners_gpu())
