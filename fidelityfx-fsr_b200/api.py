@@ -144,12 +144,18 @@ class FramePipeline:
 
     sets: list of (inp, tmp, out) images/tensors; econ/rcon: the constant blocks shared by all frames."""
 
-    def __init__(self, sets, econ, rcon, flags=0, device=None):
+    def __init__(self, sets, econ, rcon, flags=0, device=None, priorities=None):
+        """priorities: optional (easu, rcas) CUDA stream priorities (lower = more urgent); None = default streams."""
         self._L = _lib.lib()
         self._econ, self._rcon = (ctypes.c_uint32 * 16)(*econ), (ctypes.c_uint32 * 4)(*rcon)
         self._imgs = [(_as_img(a), _as_img(t), _as_img(b)) for a, t, b in sets]
         self._flags = flags
-        self.stream_easu, self.stream_rcas = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self._easu_flags = flags & ~FLAG_OUTPUT_SQUARE      # the Sample.x hook belongs to the LAST pass only
+        if priorities is None:
+            self.stream_easu, self.stream_rcas = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        else:
+            self.stream_easu = torch.cuda.Stream(device=device, priority=priorities[0])
+            self.stream_rcas = torch.cuda.Stream(device=device, priority=priorities[1])
         self._easu_done = [torch.cuda.Event() for _ in sets]
         self._rcas_done = [None for _ in sets]
 
@@ -164,7 +170,7 @@ class FramePipeline:
         sa, sb = self.stream_easu, self.stream_rcas
         if self._rcas_done[slot] is not None:
             sa.wait_event(self._rcas_done[slot])       # the slot's intermediate is free again
-        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, 0, 0, self._flags, ctypes.c_void_p(sa.cuda_stream))
+        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, 0, 0, self._easu_flags, ctypes.c_void_p(sa.cuda_stream))
         if rc:
             _lib.check(rc)
         self._easu_done[slot].record(sa)

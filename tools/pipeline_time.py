@@ -12,7 +12,12 @@ ins = [torch.from_numpy(F.to_half(F.uniform(iw, ih, 12345 + t))).cuda() for t in
 tmps = [torch.empty((oh, ow, 4), dtype=torch.float16, device="cuda") for _ in range(R)]
 outs = [torch.empty((oh, ow, 4), dtype=torch.float16, device="cuda") for _ in range(R)]
 econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
-sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+prio = os.environ.get("FSR1_PIPE_PRIO")     # e.g. "0,-1": RCAS stream more urgent than the EASU stream
+if prio:
+    pa, pb = (int(v) for v in prio.split(","))
+    sa, sb = torch.cuda.Stream(priority=pa), torch.cuda.Stream(priority=pb)
+else:
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
 easu_done = [torch.cuda.Event() for _ in range(R)]
 rcas_done = [torch.cuda.Event() for _ in range(R)]
 def run(n):

@@ -10,3 +10,7 @@ for v in 6 7 8 9; do
   FSR1_EASU_QUAD_VARIANT=$v timeout 90 python tools/variant_time.py 2x 2>&1 | tail -2
   FSR1_EASU_QUAD_VARIANT=$v timeout 90 python tools/pipeline_time.py 2>&1 | tail -1
 done
+for prio in "0,-1" "-1,0"; do
+  echo -n "stream priorities easu,rcas = $prio: "
+  FSR1_PIPE_PRIO=$prio timeout 90 python tools/pipeline_time.py 2>&1 | tail -1
+done
