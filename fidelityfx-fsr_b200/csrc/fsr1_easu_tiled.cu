@@ -528,6 +528,15 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
   auto box_x = [&](int t) { return (t % tiles_x) * kQCX - 2; };
   auto box_y = [&](int t) { return mbase + (t / tiles_x) * C::kCY - 1; };
   int t = blockIdx.x;
+  // experimental build (kFastPath): tile coordinates advance incrementally — one division per kernel instead of one
+  // per tile and thread (the persistent loop's bookkeeping is ~10 % of the instructions executed)
+  int tx = 0, ty = 0, step_x = 0, step_y = 0;
+  if constexpr (kFastPath) {
+    tx = t % tiles_x;
+    ty = t / tiles_x;
+    step_x = (int)gridDim.x % tiles_x;
+    step_y = (int)gridDim.x / tiles_x;
+  }
   if (tid == 0 && t < n_tiles) {
     mbar_expect_tx(&sm.bar[0], C::kElems * 8u);
     tma_load_2d(sm.tile[0], &tmap, box_x(t), box_y(t) - p.in.row0, &sm.bar[0]);
@@ -535,13 +544,20 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
   for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
     const int b = it & 1;
     const int tn = t + gridDim.x;
+    int txn = tx + step_x, tyn = ty + step_y;  // coordinates of tile tn (kFastPath only)
+    if (txn >= tiles_x) { txn -= tiles_x; tyn++; }
     if (tid == 0 && tn < n_tiles) {  // prefetch the next tile into the other buffer (its readers all passed
       fence_proxy_async();           // the barrier that closed the previous iteration)
       mbar_expect_tx(&sm.bar[b ^ 1], C::kElems * 8u);
-      tma_load_2d(sm.tile[b ^ 1], &tmap, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
+      if constexpr (kFastPath)
+        tma_load_2d(sm.tile[b ^ 1], &tmap, txn * kQCX - 2, mbase + tyn * C::kCY - 1 - p.in.row0, &sm.bar[b ^ 1]);
+      else
+        tma_load_2d(sm.tile[b ^ 1], &tmap, box_x(tn), box_y(tn) - p.in.row0, &sm.bar[b ^ 1]);
     }
     uint2* tile = sm.tile[b];
-    const int gx0 = box_x(t), gy0 = box_y(t);
+    const int gx0 = kFastPath ? tx * kQCX - 2 : box_x(t), gy0 = kFastPath ? mbase + ty * C::kCY - 1 : box_y(t);
+    tx = txn;
+    ty = tyn;
     mbar_wait(&sm.bar[b], (it >> 1) & 1);
     if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + C::kBH > p.in.h) {
       for (int j = warp; j < C::kBH; j += NW) {
