@@ -215,6 +215,7 @@ def run_ours(args, rank, world, local_rank):
     econ1, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(SHARPNESS)
     stream = torch.cuda.current_stream()
     out = {}
+    pipe = None   # api.FramePipeline when frames are software-pipelined on two streams (default at N=1)
     if world == 1:
         def resident(a):  # rows padded to a 16-byte multiple, like any texture allocation (TMA / 128-bit access need it)
             h, w = a.shape[:2]
@@ -264,6 +265,49 @@ def run_ours(args, rank, world, local_rank):
         elif args.no_overlap:
             def step(i):
                 ups[i % RING].upscale()
+        elif args.halo_depth > 1 or args.pipeline_sharded:
+            # EXPERIMENTAL (not the default): halo exchange `halo_depth` frames ahead (more slack against rank-to-rank
+            # jitter than the one-frame prefetch below) and, with --pipeline-sharded, RCAS of frame i on a second
+            # stream while EASU of frame i+1 runs (api.FramePipeline over the slab windows), as at N=1
+            depth = max(1, min(args.halo_depth, RING - 1))
+            comm = torch.cuda.Stream(device=dev)
+            ready = [torch.cuda.Event() for _ in range(RING)]
+            done = [torch.cuda.Event() for _ in range(RING)]
+            used = [False] * RING
+            if args.pipeline_sharded:
+                u0 = ups[0]
+                e0, e1 = u0.plan.easu_rows(rank)
+                y0, y1 = u0.plan.out_rows(rank)
+                pipe = api.FramePipeline(
+                    [(api.image(u.window, height=u.in_h, row0=u._win0), api.image(u.tmp, height=u.out_h, row0=e0),
+                      api.image(u.out, height=u.out_h, row0=y0)) for u in ups],
+                    ups[0].econ, ups[0].rcon, device=dev, easu_rows=(e0, e1), rcas_rows=(y0, y1))
+
+            def prefetch(j):
+                k = j % RING
+                if used[k]:
+                    comm.wait_event(done[k])     # frame j-RING, the window's previous reader
+                with torch.cuda.stream(comm):
+                    ups[k]._exchange()
+                    ready[k].record(comm)
+            for j in range(depth):
+                prefetch(j)
+            frame = [0]
+
+            def step(_):
+                i = frame[0]
+                frame[0] += 1
+                k = i % RING
+                prefetch(i + depth)
+                if pipe is not None:
+                    pipe.stream_easu.wait_event(ready[k])
+                    pipe.submit(k)
+                    done[k].record(pipe.stream_easu)      # EASU is the only reader of the window
+                else:
+                    stream.wait_event(ready[k])
+                    ups[k]._launch(stream)
+                    done[k].record(stream)
+                used[k] = True
         else:
             # frame pipeline: while frame i is upscaled, the halo rows of frame i+1 (already resident) travel on a
             # second stream; kernels of frame i+1 wait on that exchange's event only
@@ -318,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = api.launch_count()
-    piped = world == 1 and pipe is not None
+    piped = pipe is not None
     ms = timed(step, K, pre=(lambda: pipe.begin(stream)) if piped else None, post=(lambda: pipe.end(stream)) if piped else None)
     launches = api.launch_count() - launches0
     if world > 1 and args.graph:
@@ -401,7 +445,9 @@ def run_ours(args, rank, world, local_rank):
                        "sharpness_stops": SHARPNESS, "frame": "LCG uniform noise, seed 12345+t",
                        "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * ih + 2 * ow * oh) * bpp / 1e6),
                        "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step, %s" % (
-                           world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else "halo exchange of frame i+1 overlapped with frame i on a second stream"))},
+                           world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else (
+                               "EXPERIMENTAL: halo exchange %d frames ahead%s" % (args.halo_depth, ", RCAS/EASU of consecutive frames on two streams" if args.pipeline_sharded else "")
+                               if (args.halo_depth > 1 or args.pipeline_sharded) else "halo exchange of frame i+1 overlapped with frame i on a second stream")))},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1:
@@ -455,6 +501,8 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="N=1: run EASU and RCAS of each frame back to back on one stream (no frame overlap)")
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
+    ap.add_argument("--halo-depth", type=int, default=1, help="multi-GPU (experimental): exchange halos this many frames ahead (default 1 = the measured configuration)")
+    ap.add_argument("--pipeline-sharded", action="store_true", help="multi-GPU (experimental): overlap RCAS of frame i with EASU of frame i+1 on two streams, as at N=1")
     ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")
     args = ap.parse_args()

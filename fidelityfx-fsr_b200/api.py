@@ -144,8 +144,11 @@ class FramePipeline:
 
     sets: list of (inp, tmp, out) images/tensors; econ/rcon: the constant blocks shared by all frames."""
 
-    def __init__(self, sets, econ, rcon, flags=0, device=None, priorities=None):
-        """priorities: optional (easu, rcas) CUDA stream priorities (lower = more urgent); None = default streams."""
+    def __init__(self, sets, econ, rcon, flags=0, device=None, priorities=None, easu_rows=(0, 0), rcas_rows=(0, 0)):
+        """priorities: optional (easu, rcas) CUDA stream priorities (lower = more urgent); None = default streams.
+        easu_rows / rcas_rows: output row ranges [y0,y1) of the two passes when the images are row-slab windows
+        (EASU covers the slab plus the one-row apron RCAS reads); (0, 0) = the whole image."""
+        self._erows, self._rrows = tuple(int(v) for v in easu_rows), tuple(int(v) for v in rcas_rows)
         self._L = _lib.lib()
         self._econ, self._rcon = (ctypes.c_uint32 * 16)(*econ), (ctypes.c_uint32 * 4)(*rcon)
         self._imgs = [(_as_img(a), _as_img(t), _as_img(b)) for a, t, b in sets]
@@ -170,12 +173,14 @@ class FramePipeline:
         sa, sb = self.stream_easu, self.stream_rcas
         if self._rcas_done[slot] is not None:
             sa.wait_event(self._rcas_done[slot])       # the slot's intermediate is free again
-        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, 0, 0, self._easu_flags, ctypes.c_void_p(sa.cuda_stream))
+        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, self._erows[0], self._erows[1], self._easu_flags,
+                               ctypes.c_void_p(sa.cuda_stream))
         if rc:
             _lib.check(rc)
         self._easu_done[slot].record(sa)
         sb.wait_event(self._easu_done[slot])
-        rc = self._L.fsr1_rcas(ctypes.byref(t), ctypes.byref(b), self._rcon, 0, 0, self._flags, ctypes.c_void_p(sb.cuda_stream))
+        rc = self._L.fsr1_rcas(ctypes.byref(t), ctypes.byref(b), self._rcon, self._rrows[0], self._rrows[1], self._flags,
+                               ctypes.c_void_p(sb.cuda_stream))
         if rc:
             _lib.check(rc)
         if self._rcas_done[slot] is None:
