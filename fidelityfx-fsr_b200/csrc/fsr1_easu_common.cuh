@@ -7,6 +7,11 @@
 
 namespace fsr1 {
 
+#ifdef FSR1_CPU_EMU  // tests/emu: this device code compiled for the host; the emulator supplies the PTX wrappers
+}  // namespace fsr1
+#include "fsr1_emu_ptx.h"
+namespace fsr1 {
+#else
 // ---- PTX wrappers: mbarrier + TMA ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -38,15 +43,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+#endif  // FSR1_CPU_EMU
+
 // ---- small helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 h2c(float v) { return __float2half2_rn(v); }
+#ifndef FSR1_CPU_EMU
 __device__ __forceinline__ float rcp_approx(float a) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 }
+#endif
 
 // FsrEasuSetF without the bilinear weight: (dirX, dirY, lenX^2 + lenY^2) of the texel whose luma is lC.
 __device__ __forceinline__ float4 texel_terms(float lA, float lB, float lC, float lD, float lE) {
@@ -80,6 +89,7 @@ __device__ __forceinline__ Shape pixel_shape(float dx, float dy, float len) {
 }
 
 
+#ifndef FSR1_CPU_EMU
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -111,5 +121,7 @@ static inline int sm_count() {  // of the CURRENT device (one process may drive 
     n = 148;
   return n;
 }
+
+#endif  // FSR1_CPU_EMU
 
 }  // namespace fsr1

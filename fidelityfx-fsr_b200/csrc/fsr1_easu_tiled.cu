@@ -69,8 +69,12 @@ __device__ __forceinline__ __half2 tap_weight(__half2 d2, __half2 lob, __half2 c
 // patterns as signed 16-bit integers orders every non-negative d2 correctly and returns d2 itself when rounding made
 // it slightly negative: identical results to __hmin2 for finite inputs.
 __device__ __forceinline__ __half2 tap_weight_iclamp(__half2 d2, __half2 lob, __half2 clp) {
+#ifdef FSR1_CPU_EMU
+  const uint32_t r = emu_min_s16x2(h22u(d2), h22u(clp));
+#else
   uint32_t r;
   asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(h22u(d2)), "r"(h22u(clp)));
+#endif
   d2 = u2h2(r);
   const __half2 wb = __hfma2(__hfma2(h2c(0.25f), d2, h2c(-1.25f)), d2, h2c(1.0f));
   __half2 wa = __hfma2(lob, d2, h2c(-1.0f));
@@ -208,7 +212,11 @@ __host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
 __global__ void __launch_bounds__(kThreads, 3)
 easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH,
                     const int tiles_x, const int n_tiles) {
+#ifdef FSR1_CPU_EMU
+  unsigned char* smem_raw = fsr1_emu_dynamic_smem();
+#else
   extern __shared__ unsigned char smem_raw[];
+#endif
   // 128-byte align by OFFSET (pointer arithmetic on the shared array keeps the address space -> LDS/STS)
   unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int n = BW * BH;
@@ -601,9 +609,11 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
 // ---- warp-specialised variant: one producer warp prepares tile i+1 (TMA wait, clamp fix-up, luma, terms) while
 // NWC consumer warps run phase 3 of tile i.  No CTA-wide barrier in the steady state: the hand-offs are mbarriers
 // (ready[b]: producer -> consumers, free_[b]: consumers -> producer), tile/L/S are all double-buffered.
+#ifndef FSR1_CPU_EMU
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#endif
 
 template <int NWC> struct __align__(128) QuadWsSmem {
   uint2 tile[2][QuadCfg<NWC>::kPad];
@@ -689,6 +699,7 @@ easu_h_quad2x_ws_kernel(const EasuParams p, const __grid_constant__ CUtensorMap 
   }
 }
 
+#ifndef FSR1_CPU_EMU
 // ---- host side ----------------------------------------------------------------------------------------
 // one RGBA16F texel = one 64-bit TMA element; tensor = the stored window of the image
 static bool make_tmap(CUtensorMap* tmap, const ImgView& in, int BW, int BH) {
@@ -785,5 +796,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   *name = "easu_h_vpairs<64x32,persistent,tma2>";
   return cudaGetLastError();
 }
+
+#endif  // FSR1_CPU_EMU
 
 }  // namespace fsr1

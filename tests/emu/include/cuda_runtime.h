@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE: stands in for <cuda_runtime.h> when the device sources are compiled for the host (tests/emu)
+#pragma once
+#include "cuda_emu.h"

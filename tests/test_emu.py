@@ -1,0 +1,76 @@
+"""The device code of csrc/fsr1_easu_tiled.cu compiled for the HOST (tests/emu: one OS thread per CUDA thread, emulated
+TMA / mbarrier / half arithmetic) and checked against the oracle — kernel logic can be debugged without a GPU.
+
+What it proves on CPU, for the 2x EASU kernel family:
+  * the production variant (FSR1_EASU_QUAD_VARIANT=6) stays within the fp16 tolerance of the fp32 oracle — tiling,
+    clamp-to-edge fix-up, persistent tile loop, row ranges and image borders included;
+  * the variants prepared for measurement (7: f32x2-packed per-pixel analysis, 8: integer distance clamp, 9: predicate-free
+    interior path + incremental tile coordinates) produce the SAME BITS as the production variant.
+The GPU remains the authority on the hardware (tests/test_gpu_parity.py); this is a second, cheaper net."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fsr1_b200 as F
+import oracle_lib as ol
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_lib = None
+
+
+def emu_lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-s", "-C", EMU_DIR, "libfsr1_emu.so"])
+        _lib = ctypes.CDLL(os.path.join(EMU_DIR, "libfsr1_emu.so"))
+    return _lib
+
+
+def emu_easu(variant, src_h, ow, oh, y0=0, y1=None, ctas=3):
+    ih, iw = src_h.shape[:2]
+    y1 = oh if y1 is None else y1
+    con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
+    src = np.ascontiguousarray(src_h.view(np.uint16))
+    out = np.zeros((oh, ow, 4), np.uint16)
+    rc = emu_lib().emu_easu_h_quad2x(variant, ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
+                                     ctypes.c_void_p(out.ctypes.data), ow, oh, ctypes.c_longlong(out.strides[0]), con, y0, y1, ctas)
+    assert rc == 0
+    return out.view(np.float16)
+
+
+@pytest.mark.parametrize("size", [(64, 36), (70, 23), (33, 17), (5, 3)])
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_emulated_production_kernel_within_fp16_tolerance(size, gen):
+    iw, ih = size
+    ow, oh = 2 * iw, 2 * ih
+    src = F.to_half(getattr(F, gen)(iw, ih, 31))
+    want = ol.easu(src.astype(np.float32), ow, oh)
+    got = emu_easu(6, src, ow, oh)
+    assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 5e-3       # GPU tolerance is 1e-2; measured there <= 2.8e-3
+    assert (got[..., 3] == np.float16(1.0)).all()
+    # one CTA or many, same result (persistent tile loop, double buffering)
+    assert np.array_equal(emu_easu(6, src, ow, oh, ctas=1).view(np.uint16), got.view(np.uint16))
+
+
+def test_emulated_row_range_only_touches_its_rows():
+    iw, ih, ow, oh = 64, 36, 128, 72
+    src = F.to_half(F.uniform(iw, ih, 5))
+    full = emu_easu(6, src, ow, oh)
+    part = emu_easu(6, src, ow, oh, y0=19, y1=53)
+    assert np.array_equal(part[19:53].view(np.uint16), full[19:53].view(np.uint16))
+    assert not part[:19].view(np.uint16).any() and not part[53:].view(np.uint16).any()
+
+
+@pytest.mark.parametrize("variant", [7, 8, 9])
+def test_prepared_variants_are_bit_identical_to_production(variant):
+    for (iw, ih) in ((64, 36), (70, 23), (33, 17), (99, 40)):   # sizes whose FsrEasuCon scale is exactly 0.5 (97 is not)
+        for gen in (F.uniform, F.structured):
+            src = F.to_half(gen(iw, ih, 77))
+            base = emu_easu(6, src, 2 * iw, 2 * ih)
+            assert np.array_equal(emu_easu(variant, src, 2 * iw, 2 * ih).view(np.uint16), base.view(np.uint16))
+    src = F.to_half(F.uniform(64, 36, 6))
+    assert np.array_equal(emu_easu(variant, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16),
+                          emu_easu(6, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16))
