@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(32 * kNW) rcas_h_packed_kernel(const RcasParam
     rcas_rows<true, kClamp, kNewton, kRows>(p, x, ys, lane);
 }
 
+#ifndef FSR1_CPU_EMU  // tests/emu compiles the device code above for the host and supplies its own launcher
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name) {
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
@@ -186,5 +187,7 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
   }
   return cudaGetLastError();
 }
+
+#endif  // FSR1_CPU_EMU
 
 }  // namespace fsr1

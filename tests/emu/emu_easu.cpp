@@ -11,10 +11,22 @@ thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 gridDim, blockDim;
 static pthread_barrier_t g_cta_barrier;
 void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
+// warp shuffles: per-warp exchange buffer between two warp-wide barriers (initialised per CTA by run_cta)
+static pthread_barrier_t g_warp_barrier[32];
+static uint32_t g_shfl_buf[32][32];
+uint32_t fsr1_emu_shfl(uint32_t v, int src) {
+  const int w = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  g_shfl_buf[w][lane] = v;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  const uint32_t r = src < 0 ? v : g_shfl_buf[w][src];
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  return r;
+}
 alignas(128) static unsigned char g_dynamic_smem[232448];
 unsigned char* fsr1_emu_dynamic_smem() { return g_dynamic_smem; }
 
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_easu_tiled.cu"
+#include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_packed.cu"
 
 using namespace fsr1;
 
@@ -70,3 +82,80 @@ extern "C" int emu_easu_h_quad2x(int variant, const void* in, int iw, int ih, lo
   }
   return 0;
 }
+
+// launch_easu_h_tiled's generic branch: largest footprint (in texels) any tile needs along one axis
+static int max_footprint(int n_out, int first, int tile, float scale, float offset, bool even_origin) {
+  int best = 4;
+  for (int o0 = first; o0 < n_out; o0 += tile) {
+    const int o1 = (o0 + tile - 1 < n_out - 1) ? o0 + tile - 1 : n_out - 1;
+    int origin = cell_of(o0, scale, offset) - 1;
+    if (even_origin) origin &= ~1;
+    const int span = cell_of(o1, scale, offset) + 2 - origin + 1;
+    if (span > best) best = span;
+  }
+  return best;
+}
+
+// The any-scale kernel (easu_h_pairs_kernel: vertical pixel pairs, 64x32 tiles).  Returns 0, -1 if unsupported.
+extern "C" int emu_easu_h_pairs(const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
+                                long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
+  EasuParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
+  p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
+  memcpy(&p.c0x, &con[0], 4); memcpy(&p.c0y, &con[1], 4); memcpy(&p.c0z, &con[2], 4); memcpy(&p.c0w, &con[3], 4);
+  p.y0 = y0; p.y1 = y1;
+  if (!(p.c0x > 0.0f && p.c0x <= 1.0f && p.c0y > 0.0f && p.c0y <= 1.0f)) return -1;
+  int BW = max_footprint(ow, 0, kTileW, p.c0x, p.c0z, true);
+  const int BH = max_footprint(y1, y0, kTileH, p.c0y, p.c0w, false);
+  BW = (BW + 1) & ~1;
+  if (BW > 256 || BH > 256 || pairs_smem_bytes(BW, BH) > sizeof g_dynamic_smem) return -1;
+  const int tiles_x = (ow + kTileW - 1) / kTileW, n_tiles = tiles_x * ((y1 - y0 + kTileH - 1) / kTileH);
+  const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+  CUtensorMap tmap{(const unsigned char*)in, iw, ih, in_pitch, BW, BH, 8};
+  for (int b = 0; b < grid; b++) {
+    pthread_barrier_init(&g_cta_barrier, nullptr, (unsigned)kThreads);
+    std::vector<std::thread> ts;
+    for (int t = 0; t < kThreads; t++)
+      ts.emplace_back([=, &p, &tmap]() {
+        threadIdx = uint3{(unsigned)t, 0, 0};
+        blockIdx = uint3{(unsigned)b, 0, 0};
+        gridDim.x = (unsigned)grid;
+        blockDim.x = (unsigned)kThreads;
+        easu_h_pairs_kernel(p, tmap, BW, BH, tiles_x, n_tiles);
+      });
+    for (auto& th : ts) th.join();
+    pthread_barrier_destroy(&g_cta_barrier);
+  }
+  return 0;
+}
+
+// The production RCAS kernel (rcas_h_packed_kernel<kClamp, mufu, 4 rows, 4 warps>): grid = 60-pixel spans x 16-row bands.
+extern "C" int emu_rcas_h_packed(const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                                 const uint32_t* con, int clamp, int y0, int y1) {
+  RcasParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
+  p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
+  memcpy(&p.sharp, &con[0], 4);
+  p.sharp_h2 = con[1];
+  p.y0 = y0; p.y1 = y1; p.clamp = clamp; p.options = 0;
+  constexpr int NWARP = 4, ROWS = 4, threads = 32 * NWARP;
+  const int gx = (w + kSpan - 1) / kSpan, gy = (y1 - y0 + NWARP * ROWS - 1) / (NWARP * ROWS);
+  for (int by = 0; by < gy; by++)
+    for (int bx = 0; bx < gx; bx++) {
+      for (int i = 0; i < NWARP; i++) pthread_barrier_init(&g_warp_barrier[i], nullptr, 32);
+      std::vector<std::thread> ts;
+      for (int t = 0; t < threads; t++)
+        ts.emplace_back([=, &p]() {
+          threadIdx = uint3{(unsigned)t, 0, 0};
+          blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
+          gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
+          blockDim.x = (unsigned)threads;
+          if (clamp) rcas_h_packed_kernel<true, false, ROWS, NWARP>(p);
+          else rcas_h_packed_kernel<false, false, ROWS, NWARP>(p);
+        });
+      for (auto& th : ts) th.join();
+      for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
+    }
+  return 0;
+}
+

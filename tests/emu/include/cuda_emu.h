@@ -91,6 +91,27 @@ inline __half hmax1(__half a, __half b) { return f2h(fmaxf(h2f(a), h2f(b))); }
 inline __half2 __hmin2(__half2 a, __half2 b) { return mkh2(hmin1(a.x, b.x), hmin1(a.y, b.y)); }
 inline __half2 __hmax2(__half2 a, __half2 b) { return mkh2(hmax1(a.x, b.x), hmax1(a.y, b.y)); }
 
+inline __half2 h2rcp(__half2 a) { return mkh2(f2h(1.0f / h2f(a.x)), f2h(1.0f / h2f(a.y))); }
+
+// ---- integer / warp intrinsics ---------------------------------------------------------------------------
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+  const uint64_t v = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
+// All 32 lanes of a warp must call these together (true for the kernels emulated here): exchange through a per-warp
+// buffer between two warp-wide barriers.
+uint32_t fsr1_emu_shfl(uint32_t v, int src_lane_or_negative_for_self);
+inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta) {
+  const int lane = (int)(threadIdx.x & 31);
+  return fsr1_emu_shfl(v, lane >= (int)delta ? lane - (int)delta : -1);
+}
+inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned delta) {
+  const int lane = (int)(threadIdx.x & 31);
+  return fsr1_emu_shfl(v, lane + (int)delta < 32 ? lane + (int)delta : -1);
+}
+
 // ---- emulated TMA descriptor + mbarrier (see fsr1_emu_ptx.h) ----------------------------------------------
 struct CUtensorMap {
   const unsigned char* base;

@@ -1,4 +1,4 @@
-"""The device code of csrc/fsr1_easu_tiled.cu compiled for the HOST (tests/emu: one OS thread per CUDA thread, emulated
+"""The device code of csrc/fsr1_easu_tiled.cu and csrc/fsr1_rcas_packed.cu compiled for the HOST (tests/emu: one OS thread per CUDA thread, emulated
 TMA / mbarrier / half arithmetic) and checked against the oracle — kernel logic can be debugged without a GPU.
 
 What it proves on CPU, for the 2x EASU kernel family:
@@ -74,3 +74,64 @@ def test_prepared_variants_are_bit_identical_to_production(variant):
     src = F.to_half(F.uniform(64, 36, 6))
     assert np.array_equal(emu_easu(variant, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16),
                           emu_easu(6, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16))
+
+
+def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2):
+    ih, iw = src_h.shape[:2]
+    y1 = oh if y1 is None else y1
+    con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
+    src = np.ascontiguousarray(src_h.view(np.uint16))
+    out = np.zeros((oh, ow, 4), np.uint16)
+    rc = emu_lib().emu_easu_h_pairs(ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
+                                    ctypes.c_void_p(out.ctypes.data), ow, oh, ctypes.c_longlong(out.strides[0]), con, y0, y1, ctas)
+    assert rc == 0
+    return out.view(np.float16)
+
+
+@pytest.mark.parametrize("shape", [(96, 54, 144, 81), (96, 54, 125, 70), (64, 64, 64, 64), (50, 20, 65, 26), (33, 17, 57, 31),
+                                   (64, 36, 128, 72), (96, 54, 192, 81)])
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_emulated_any_scale_kernel_within_fp16_tolerance(shape, gen):
+    """easu_h_pairs_kernel (1.5x, 1.3x, 1x, ragged sizes, 2x through the generic path, x2.0/y1.5): vertical pixel pairs
+    sharing or not sharing an input cell row, box footprints computed per launch, even-aligned box origins."""
+    iw, ih, ow, oh = shape
+    src = F.to_half(getattr(F, gen)(iw, ih, 31))
+    want = ol.easu(src.astype(np.float32), ow, oh)
+    got = emu_easu_pairs(src, ow, oh)
+    assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 5e-3
+    y0, y1 = oh // 3, 2 * oh // 3 + 1
+    part = emu_easu_pairs(src, ow, oh, y0=y0, y1=y1, ctas=1)
+    assert np.array_equal(part[y0:y1].view(np.uint16), got[y0:y1].view(np.uint16))
+    assert not part[:y0].view(np.uint16).any() and not part[y1:].view(np.uint16).any()
+
+
+def emu_rcas(src_h, sharp, clamp=False, y0=0, y1=None):
+    h, w = src_h.shape[:2]
+    y1 = h if y1 is None else y1
+    con = (ctypes.c_uint32 * 4)(*ol.rcas_con(sharp))
+    src = np.ascontiguousarray(src_h.view(np.uint16))
+    out = np.zeros((h, w, 4), np.uint16)
+    rc = emu_lib().emu_rcas_h_packed(ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(out.ctypes.data), w, h,
+                                     ctypes.c_longlong(src.strides[0]), ctypes.c_longlong(out.strides[0]), con, 1 if clamp else 0, y0, y1)
+    assert rc == 0
+    return out.view(np.float16)
+
+
+@pytest.mark.parametrize("size", [(128, 72), (61, 19), (200, 33), (6, 5)])
+@pytest.mark.parametrize("clamp", [False, True])
+def test_emulated_rcas_kernel_within_fp16_tolerance(size, clamp):
+    """rcas_h_packed_kernel: two pixels per lane, neighbours by warp shuffle, 60-pixel spans overlapping by 4, the unchecked
+    interior path and the checked border path, out-of-image taps reading 0 or clamped."""
+    w, h = size
+    for gen in (F.uniform, F.structured):
+        src = F.to_half(gen(w, h, 9))
+        for sharp in (0.0, 0.25, 2.0):
+            want = ol.rcas(src.astype(np.float32), ol.rcas_con(sharp), clamp)
+            got = emu_rcas(src, sharp, clamp)
+            assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 4e-3, (gen.__name__, sharp)
+    y0, y1 = h // 3, 2 * h // 3 + 1
+    part = emu_rcas(src, 0.25, clamp, y0=y0, y1=y1)
+    full = emu_rcas(src, 0.25, clamp)
+    assert np.array_equal(part[y0:y1].view(np.uint16), full[y0:y1].view(np.uint16))
+    assert not part[:y0].view(np.uint16).any() and not part[y1:].view(np.uint16).any()
+
