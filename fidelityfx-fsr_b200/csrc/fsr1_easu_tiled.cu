@@ -95,6 +95,38 @@ __device__ __forceinline__ __half2 tap_weight_unclamped(__half2 d2, __half2 lob)
   return __hmul2(wb, wa);
 }
 
+// ---- experimental (FSR1_EASU_QUAD_VARIANT=7, not yet measured): the per-pixel fp32 analysis of a pixel PAIR in
+// packed f32x2 (FFMA2 / FMUL2 / FADD2 issue at the scalar FFMA rate on B200, profiles/r01_ubench_pipes.txt, so this
+// halves the fp32 FMA-class instructions of phase 3).  Lane .x = pixel A, .y = pixel B; the operations per lane are
+// exactly those of pixel_shape().
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+struct Shape2 { float2 qa, qb, qc, lob, clp; };
+__device__ __forceinline__ Shape2 pixel_shape2(float2 dx, float2 dy, float2 len) {
+  const float2 dirR = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+  const bool zx = dirR.x < (1.0f / 32768.0f), zy = dirR.y < (1.0f / 32768.0f);
+  const float2 rs = mk2(zx ? 1.0f : prx_lo_rsq(dirR.x), zy ? 1.0f : prx_lo_rsq(dirR.y));
+  dx = __fmul2_rn(mk2(zx ? 1.0f : dx.x, zy ? 1.0f : dx.y), rs);
+  dy = __fmul2_rn(dy, rs);
+  len = __fmul2_rn(len, bc2(0.5f));
+  len = __fmul2_rn(len, len);
+  const float2 dx2 = __fmul2_rn(dx, dx), dy2 = __fmul2_rn(dy, dy);
+  const float2 rmax = mk2(prx_lo_rcp(fmaxf(fabsf(dx.x), fabsf(dy.x))), prx_lo_rcp(fmaxf(fabsf(dx.y), fabsf(dy.y))));
+  const float2 stretch = __fmul2_rn(__fadd2_rn(dx2, dy2), rmax);
+  const float2 l2x = __ffma2_rn(__fadd2_rn(stretch, bc2(-1.0f)), len, bc2(1.0f));
+  const float2 l2y = __ffma2_rn(bc2(-0.5f), len, bc2(1.0f));
+  Shape2 s;
+  s.lob = __ffma2_rn(bc2((float)((1.0 / 4.0 - 0.04) - 0.5)), len, bc2(0.5f));
+  s.clp = mk2(prx_lo_rcp(s.lob.x), prx_lo_rcp(s.lob.y));
+  const float2 X2 = __fmul2_rn(l2x, l2x), Y2 = __fmul2_rn(l2y, l2y);
+  s.qa = __ffma2_rn(X2, dx2, __fmul2_rn(Y2, dy2));
+  s.qc = __ffma2_rn(X2, dy2, __fmul2_rn(Y2, dx2));
+  s.qb = __fmul2_rn(__fmul2_rn(__fmul2_rn(dx, dy), bc2(2.0f)), __ffma2_rn(Y2, bc2(-1.0f), X2));
+  return s;
+}
+__device__ __forceinline__ Shape lane_x(const Shape2& s) { return Shape{s.qa.x, s.qb.x, s.qc.x, s.lob.x, s.clp.x}; }
+__device__ __forceinline__ Shape lane_y(const Shape2& s) { return Shape{s.qa.y, s.qb.y, s.qc.y, s.lob.y, s.clp.y}; }
+
 // =======================================================================================================
 //  generic kernel: any scale, lane = pixel pair (2*lane, 2*lane+1), rows warp and warp+8 of a 64x16 tile
 // =======================================================================================================
@@ -102,13 +134,27 @@ constexpr int kTileW = 64, kTileH = 32;
 
 // One vertical pixel pair of the generic kernel: pixel A (row oy) and B (row oy+1) in the same output column.
 // t0/q0 point at tap (0,0) / texel f of pixel A; DR = fy(B) - fy(A) in {0,1}.  Packed lanes are (A, B).
-template <int DR>
+// kVar = 1 (experimental, FSR1_EASU_PAIRS_VARIANT=1, validated on the CPU emulator, not yet timed): the fp32 analysis of
+// the pair packed in f32x2, the factored tap distance ox (qa ox + qb oy) + qc oy^2 and the integer distance clamp.
+template <int DR, int kVar = 0>
 __device__ __forceinline__ void vpair(const uint2* __restrict__ t0, const float4* __restrict__ q0, int BW, int SW, float ppx,
                                       float ppyA, float ppyB, uint2& outA, uint2& outB) {
   // fp32: blend of the f,g,j,k terms (reference order) and the filter shape, per pixel
   const float4 f = q0[0], g = q0[1], j = q0[SW], k = q0[SW + 1];
   const float ipx = 1.0f - ppx;
   Shape sA, sB;
+  if constexpr (kVar == 1) {
+    const float4 f2 = DR ? j : f, g2 = DR ? k : g, j2 = DR ? q0[2 * SW] : j, k2 = DR ? q0[2 * SW + 1] : k;
+    const float2 ppy = mk2(ppyA, ppyB), ipy = __ffma2_rn(ppy, bc2(-1.0f), bc2(1.0f));
+    const float2 wf = __fmul2_rn(bc2(ipx), ipy), wg = __fmul2_rn(bc2(ppx), ipy);
+    const float2 wj = __fmul2_rn(bc2(ipx), ppy), wk = __fmul2_rn(bc2(ppx), ppy);
+#define FSR1_BLEND2(C)                                                                                                  \
+  __ffma2_rn(mk2(k.C, k2.C), wk, __ffma2_rn(mk2(j.C, j2.C), wj, __ffma2_rn(mk2(g.C, g2.C), wg, __fmul2_rn(mk2(f.C, f2.C), wf))))
+    const Shape2 s2 = pixel_shape2(FSR1_BLEND2(x), FSR1_BLEND2(y), FSR1_BLEND2(z));
+#undef FSR1_BLEND2
+    sA = lane_x(s2);
+    sB = lane_y(s2);
+  } else {
   {
     const float ipy = 1.0f - ppyA, wf = ipx * ipy, wg = ppx * ipy, wj = ipx * ppyA, wk = ppx * ppyA;
     sA = pixel_shape(fmaf(k.x, wk, fmaf(j.x, wj, fmaf(g.x, wg, f.x * wf))), fmaf(k.y, wk, fmaf(j.y, wj, fmaf(g.y, wg, f.y * wf))),
@@ -120,20 +166,35 @@ __device__ __forceinline__ void vpair(const uint2* __restrict__ t0, const float4
     sB = pixel_shape(fmaf(k2.x, wk, fmaf(j2.x, wj, fmaf(g2.x, wg, f2.x * wf))), fmaf(k2.y, wk, fmaf(j2.y, wj, fmaf(g2.y, wg, f2.y * wf))),
                      fmaf(k2.z, wk, fmaf(j2.z, wj, fmaf(g2.z, wg, f2.z * wf))));
   }
+  }
   const __half2 qa = __floats2half2_rn(sA.qa, sB.qa), qb = __floats2half2_rn(sA.qb, sB.qb);
   const __half2 qc = __floats2half2_rn(sA.qc, sB.qc), lob = __floats2half2_rn(sA.lob, sB.lob);
   const __half2 clp = __floats2half2_rn(sA.clp, sB.clp);
   // d2(k,r) = PX[k] + QY[r] + SB[k]*OY[r]; the column offset is the same for both pixels, the row offset is not
   const __half2 ppy2 = __floats2half2_rn(ppyA, ppyB), ppx2 = __float2half2_rn(ppx);
+  // kVar = 0: PX/SB per column, QY/OY per row.  kVar = 1: PX holds ox_K, SB is unused, OY holds qb*oy_R, QY qc*oy_R^2.
   __half2 PX[4], SB[4], QY[4], OY[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const __half2 oxk = __hsub2(h2c((float)(i - 1)), ppx2);
+    if constexpr (kVar == 1) {
+      const __half2 oyr = __hsub2(h2c((float)(i - 1)), ppy2);
+      PX[i] = oxk;
+      SB[i] = oxk;
+      OY[i] = __hmul2(qb, oyr);
+      QY[i] = __hmul2(__hmul2(qc, oyr), oyr);
+    } else {
     SB[i] = __hmul2(qb, oxk);
     PX[i] = __hmul2(__hmul2(qa, oxk), oxk);
     OY[i] = __hsub2(h2c((float)(i - 1)), ppy2);
     QY[i] = __hmul2(__hmul2(qc, OY[i]), OY[i]);
+    }
   }
+  // squared tap distance of tap (R,K) and its window weight
+  auto tapw = [&](int R, int K) -> __half2 {
+    if constexpr (kVar == 1) return tap_weight_iclamp(__hfma2(__hfma2(qa, PX[K], OY[R]), PX[K], QY[R]), lob, clp);
+    else return tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);
+  };
   const __half2 kZero = h2c(0.0f), one = h2c(1.0f);
   if (DR == 0) {
     // same window for both pixels: colour accumulators in structure-of-arrays form (A,B) per channel
@@ -141,7 +202,7 @@ __device__ __forceinline__ void vpair(const uint2* __restrict__ t0, const float4
 #define FSR1_VTAP0(R, K)                                                                     \
     {                                                                                        \
       const uint2 c = t0[(R) * BW + (K)];                                                    \
-      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);  \
+      const __half2 w = tapw(R, K);                                                          \
       aR = __hfma2(__low2half2(u2h2(c.x)), w, aR);                                           \
       aG = __hfma2(__high2half2(u2h2(c.x)), w, aG);                                          \
       aB = __hfma2(__low2half2(u2h2(c.y)), w, aB);                                           \
@@ -169,7 +230,7 @@ __device__ __forceinline__ void vpair(const uint2* __restrict__ t0, const float4
 #define FSR1_VTAP1(R, K)                                                                     \
     {                                                                                        \
       const uint2 ca = t0[(R) * BW + (K)], cb = t0[((R) + 1) * BW + (K)];                    \
-      const __half2 w = tap_weight(__hfma2(SB[K], OY[R], __hadd2(PX[K], QY[R])), lob, clp);  \
+      const __half2 w = tapw(R, K);                                                          \
       const __half2 wA2 = __low2half2(w), wB2 = __high2half2(w);                             \
       aRG_A = __hfma2(u2h2(ca.x), wA2, aRG_A);                                               \
       aBA_A = __hfma2(u2h2(ca.y), wA2, aBA_A);                                               \
@@ -209,6 +270,7 @@ __host__ __device__ inline size_t pairs_smem_bytes(int BW, int BH) {
   return off + 16 + 128;  // + barriers + slack for the manual 128B alignment
 }
 
+template <int kVar>
 __global__ void __launch_bounds__(kThreads, 3)
 easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int BW, const int BH,
                     const int tiles_x, const int n_tiles) {
@@ -308,8 +370,8 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
     const uint2* t0 = tile + (fyA - fy0 - 1) * BW + (fx - fx0 - 1);       // window origin: tap (0,0) of pixel A
     const float4* q0 = S + (fyA - fy0 - 1) * SW + (fx - fx0 - 1);          // term vector of texel f of pixel A
     uint2 oA, oB;
-    if (fyB == fyA) vpair<0>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
-    else vpair<1>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
+    if (fyB == fyA) vpair<0, kVar>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
+    else vpair<1, kVar>(t0, q0, BW, SW, ppx, ppyA, ppyB, oA, oB);
     if (active) {
       unsigned char* o = p.out.base + (long long)(oyA - p.out.row0) * p.out.pitch + (long long)ox * 8;
       *reinterpret_cast<uint2*>(o) = oA;
@@ -397,38 +459,6 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
   outA = make_uint2(h22u(__lows2half2(oR, oG)), h22u(__lows2half2(oB, one)));
   outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
 }
-
-// ---- experimental (FSR1_EASU_QUAD_VARIANT=7, not yet measured): the per-pixel fp32 analysis of a pixel PAIR in
-// packed f32x2 (FFMA2 / FMUL2 / FADD2 issue at the scalar FFMA rate on B200, profiles/r01_ubench_pipes.txt, so this
-// halves the fp32 FMA-class instructions of phase 3).  Lane .x = pixel A, .y = pixel B; the operations per lane are
-// exactly those of pixel_shape().
-__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
-struct Shape2 { float2 qa, qb, qc, lob, clp; };
-__device__ __forceinline__ Shape2 pixel_shape2(float2 dx, float2 dy, float2 len) {
-  const float2 dirR = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-  const bool zx = dirR.x < (1.0f / 32768.0f), zy = dirR.y < (1.0f / 32768.0f);
-  const float2 rs = mk2(zx ? 1.0f : prx_lo_rsq(dirR.x), zy ? 1.0f : prx_lo_rsq(dirR.y));
-  dx = __fmul2_rn(mk2(zx ? 1.0f : dx.x, zy ? 1.0f : dx.y), rs);
-  dy = __fmul2_rn(dy, rs);
-  len = __fmul2_rn(len, bc2(0.5f));
-  len = __fmul2_rn(len, len);
-  const float2 dx2 = __fmul2_rn(dx, dx), dy2 = __fmul2_rn(dy, dy);
-  const float2 rmax = mk2(prx_lo_rcp(fmaxf(fabsf(dx.x), fabsf(dy.x))), prx_lo_rcp(fmaxf(fabsf(dx.y), fabsf(dy.y))));
-  const float2 stretch = __fmul2_rn(__fadd2_rn(dx2, dy2), rmax);
-  const float2 l2x = __ffma2_rn(__fadd2_rn(stretch, bc2(-1.0f)), len, bc2(1.0f));
-  const float2 l2y = __ffma2_rn(bc2(-0.5f), len, bc2(1.0f));
-  Shape2 s;
-  s.lob = __ffma2_rn(bc2((float)((1.0 / 4.0 - 0.04) - 0.5)), len, bc2(0.5f));
-  s.clp = mk2(prx_lo_rcp(s.lob.x), prx_lo_rcp(s.lob.y));
-  const float2 X2 = __fmul2_rn(l2x, l2x), Y2 = __fmul2_rn(l2y, l2y);
-  s.qa = __ffma2_rn(X2, dx2, __fmul2_rn(Y2, dy2));
-  s.qc = __ffma2_rn(X2, dy2, __fmul2_rn(Y2, dx2));
-  s.qb = __fmul2_rn(__fmul2_rn(__fmul2_rn(dx, dy), bc2(2.0f)), __ffma2_rn(Y2, bc2(-1.0f), X2));
-  return s;
-}
-__device__ __forceinline__ Shape lane_x(const Shape2& s) { return Shape{s.qa.x, s.qb.x, s.qc.x, s.lob.x, s.clp.x}; }
-__device__ __forceinline__ Shape lane_y(const Shape2& s) { return Shape{s.qa.y, s.qb.y, s.qc.y, s.lob.y, s.clp.y}; }
 
 // Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
 // k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
@@ -784,16 +814,24 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   const size_t smem = pairs_smem_bytes(BW, BH);
   if (smem > 200 * 1024) return cudaErrorNotSupported;
   if (!make_tmap(&tmap, p.in, BW, BH)) return cudaErrorNotSupported;
+  static const int pairs_variant = env_knob("FSR1_EASU_PAIRS_VARIANT", 0);  // 1: experimental (see vpair)
   if (smem > 48 * 1024) {  // per device and cheap: set on every launch that needs the opt-in
-    cudaError_t e = cudaFuncSetAttribute(easu_h_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pairs_variant == 1
+                        ? cudaFuncSetAttribute(easu_h_pairs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(easu_h_pairs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const int tiles_x = (p.out.w + kTileW - 1) / kTileW, n_tiles = tiles_x * ((p.y1 - p.y0 + kTileH - 1) / kTileH);
   int per_sm = 3;
   while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 220 * 1024) per_sm--;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
-  easu_h_pairs_kernel<<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
-  *name = "easu_h_vpairs<64x32,persistent,tma2>";
+  if (pairs_variant == 1) {
+    easu_h_pairs_kernel<1><<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
+    *name = "easu_h_vpairs<64x32,persistent,tma2,f32x2shape,iclamp>";
+  } else {
+    easu_h_pairs_kernel<0><<<grid, kThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
+    *name = "easu_h_vpairs<64x32,persistent,tma2>";
+  }
   return cudaGetLastError();
 }
 

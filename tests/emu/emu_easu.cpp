@@ -97,8 +97,9 @@ static int max_footprint(int n_out, int first, int tile, float scale, float offs
 }
 
 // The any-scale kernel (easu_h_pairs_kernel: vertical pixel pairs, 64x32 tiles).  Returns 0, -1 if unsupported.
-extern "C" int emu_easu_h_pairs(const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
+extern "C" int emu_easu_h_pairs(int variant, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
                                 long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
+  if (variant != 0 && variant != 1) return -1;
   EasuParams p;
   p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
   p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
@@ -121,7 +122,8 @@ extern "C" int emu_easu_h_pairs(const void* in, int iw, int ih, long long in_pit
         blockIdx = uint3{(unsigned)b, 0, 0};
         gridDim.x = (unsigned)grid;
         blockDim.x = (unsigned)kThreads;
-        easu_h_pairs_kernel(p, tmap, BW, BH, tiles_x, n_tiles);
+        if (variant == 1) easu_h_pairs_kernel<1>(p, tmap, BW, BH, tiles_x, n_tiles);
+        else easu_h_pairs_kernel<0>(p, tmap, BW, BH, tiles_x, n_tiles);
       });
     for (auto& th : ts) th.join();
     pthread_barrier_destroy(&g_cta_barrier);

@@ -76,13 +76,13 @@ def test_prepared_variants_are_bit_identical_to_production(variant):
                           emu_easu(6, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16))
 
 
-def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2):
+def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2, variant=0):
     ih, iw = src_h.shape[:2]
     y1 = oh if y1 is None else y1
     con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
     src = np.ascontiguousarray(src_h.view(np.uint16))
     out = np.zeros((oh, ow, 4), np.uint16)
-    rc = emu_lib().emu_easu_h_pairs(ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
+    rc = emu_lib().emu_easu_h_pairs(variant, ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
                                     ctypes.c_void_p(out.ctypes.data), ow, oh, ctypes.c_longlong(out.strides[0]), con, y0, y1, ctas)
     assert rc == 0
     return out.view(np.float16)
@@ -91,16 +91,17 @@ def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2):
 @pytest.mark.parametrize("shape", [(96, 54, 144, 81), (96, 54, 125, 70), (64, 64, 64, 64), (50, 20, 65, 26), (33, 17, 57, 31),
                                    (64, 36, 128, 72), (96, 54, 192, 81)])
 @pytest.mark.parametrize("gen", ["uniform", "structured"])
-def test_emulated_any_scale_kernel_within_fp16_tolerance(shape, gen):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emulated_any_scale_kernel_within_fp16_tolerance(shape, gen, variant):
     """easu_h_pairs_kernel (1.5x, 1.3x, 1x, ragged sizes, 2x through the generic path, x2.0/y1.5): vertical pixel pairs
     sharing or not sharing an input cell row, box footprints computed per launch, even-aligned box origins."""
     iw, ih, ow, oh = shape
     src = F.to_half(getattr(F, gen)(iw, ih, 31))
     want = ol.easu(src.astype(np.float32), ow, oh)
-    got = emu_easu_pairs(src, ow, oh)
+    got = emu_easu_pairs(src, ow, oh, variant=variant)       # variant 1 = FSR1_EASU_PAIRS_VARIANT=1 (prepared, not yet timed)
     assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 5e-3
     y0, y1 = oh // 3, 2 * oh // 3 + 1
-    part = emu_easu_pairs(src, ow, oh, y0=y0, y1=y1, ctas=1)
+    part = emu_easu_pairs(src, ow, oh, y0=y0, y1=y1, ctas=1, variant=variant)
     assert np.array_equal(part[y0:y1].view(np.uint16), got[y0:y1].view(np.uint16))
     assert not part[:y0].view(np.uint16).any() and not part[y1:].view(np.uint16).any()
 

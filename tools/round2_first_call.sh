@@ -14,3 +14,8 @@ for prio in "0,-1" "-1,0"; do
   echo -n "stream priorities easu,rcas = $prio: "
   FSR1_PIPE_PRIO=$prio timeout 90 python tools/pipeline_time.py 2>&1 | tail -1
 done
+for v in 0 1; do
+  echo "== FSR1_EASU_PAIRS_VARIANT=$v (any-scale kernel; 1 = packed fp32 analysis + factored distance + integer clamp)"
+  FSR1_EASU_PAIRS_VARIANT=$v timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "fp16_kernels or golden or end_to_end or slabs or dynamic" 2>&1 | tail -1
+  for s in 1.5x 1.3x; do FSR1_EASU_PAIRS_VARIANT=$v timeout 90 python tools/variant_time.py $s 2>&1 | tail -1; done
+done
