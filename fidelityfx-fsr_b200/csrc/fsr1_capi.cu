@@ -178,6 +178,9 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
     if (e == cudaErrorNotSupported) e = launch_easu_h_tiled(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_easu_f32_tiled(p, s, &name);
+  } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
+             !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    e = launch_easu_u_tiled(p, (int)in->format, s, &name);
   }
   if (e == cudaErrorNotSupported) e = launch_easu_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);
@@ -222,6 +225,9 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
     e = launch_rcas_h_packed(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_rcas_f32_packed(p, s, &name);
+  } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
+             !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    e = launch_rcas_u_packed(p, (int)in->format, s, &name);
   }
   if (e == cudaErrorNotSupported) e = launch_rcas_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);

@@ -159,6 +159,9 @@ cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cuda
 // meet their alignment needs (the caller then falls back to the direct kernels).
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name);
+// UNORM images through TMA-tiled kernels (experimental, FSR1_UNORM_TILED=1): cudaErrorNotSupported unless enabled and applicable
+cudaError_t launch_easu_u_tiled(const EasuParams& p, int format, cudaStream_t s, const char** name);
+cudaError_t launch_rcas_u_packed(const RcasParams& p, int format, cudaStream_t s, const char** name);
 cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name);  // RGBA32F, exactly 2x
 cudaError_t launch_easu_h_precise(const EasuParams& p, cudaStream_t s, const char** name);  // RGBA16F io, fp32 math, 2x
 cudaError_t launch_rcas_f32_packed(const RcasParams& p, cudaStream_t s, const char** name);

@@ -460,11 +460,32 @@ __device__ __forceinline__ void quad_pair(const uint2 (&t)[4][4], const Shape& s
   outB = make_uint2(h22u(__highs2half2(oR, oG)), h22u(__highs2half2(oB, one)));
 }
 
+// ---- output storage of the experimental 2x kernels: RGBA16F (8 B/px) or UNORM (4 B/px) --------------------------
+struct StoreHalf {
+  static constexpr int kBpp = 8;
+  static __device__ __forceinline__ void put(unsigned char* o, uint2 v, bool ok) {
+    if (ok) *reinterpret_cast<uint2*>(o) = v;
+  }
+};
+// kBits = 8: R8G8B8A8_UNORM, 10: R10G10B10A2_UNORM.  x * (2^n - 1) + 1024 lands in [1024, 2048), where the ulp of a half
+// is 1: one HFMA2 rounds to the nearest code value and leaves it in the low mantissa bits (alpha 1.0 -> all ones).
+template <int kBits> struct StoreUnorm {
+  static constexpr int kBpp = 4;
+  static __device__ __forceinline__ void put(unsigned char* o, uint2 v, bool ok) {
+    const __half2 sc = h2c(kBits == 8 ? 255.0f : 1023.0f), k1024 = h2c(1024.0f);
+    const uint32_t t0 = h22u(__hfma2(u2h2(v.x), sc, k1024)), t1 = h22u(__hfma2(u2h2(v.y), sc, k1024));
+    uint32_t w;
+    if (kBits == 8) w = __byte_perm(t0, t1, 0x6420);  // R, G = bytes 0, 2 of t0; B, A = bytes 0, 2 of t1
+    else w = (t0 & 0x3ffu) | (((t0 >> 16) & 0x3ffu) << 10) | ((t1 & 0x3ffu) << 20) | 0xC0000000u;
+    if (ok) *reinterpret_cast<uint32_t*>(o) = w;
+  }
+};
+
 // Phase 3 for one lane and one cell row r of a 2x tile: the quad of output pixels (2k+1,2k+2)x(2m+1,2m+2) of cell
 // k = gx0+1+lane, m = gy0+1+r.  tile/S = the tile's texels and per-texel terms in shared memory.
 // kFast (experimental, FSR1_EASU_QUAD_VARIANT=9): the tile lies strictly inside the image and the row range, so every
 // bounds predicate is true and is dropped at compile time.
-template <int kTap = 0, bool kFast = false>
+template <int kTap = 0, bool kFast = false, typename ST = StoreHalf>
 __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __restrict__ tile, const float4* __restrict__ S,
                                           int gx0, int gy0, int lane, int r) {
   const int oxA = (gx0 + 1 + lane) * 2 + 1;  // cell k = gx0 + 1 + lane -> output columns 2k+1, 2k+2
@@ -495,7 +516,7 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
       const float2 Tz = __ffma2_rn(bc2(g.z), wG, __fmul2_rn(bc2(f.z), wF));
       const float2 Bx = __ffma2_rn(bc2(k.x), wG, __fmul2_rn(bc2(j.x), wF)), By = __ffma2_rn(bc2(k.y), wG, __fmul2_rn(bc2(j.y), wF));
       const float2 Bz = __ffma2_rn(bc2(k.z), wG, __fmul2_rn(bc2(j.z), wF));
-      unsigned char* orow2 = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
+      unsigned char* orow2 = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * ST::kBpp;
       const bool okA2 = kFast || oxA >= 0, okB2 = kFast || oxA + 1 < p.out.w;
       uint2 oA2, oB2;
       if (rowT) {
@@ -503,16 +524,16 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
                                        __ffma2_rn(By, bc2(0.25f), __fmul2_rn(Ty, bc2(0.75f))),
                                        __ffma2_rn(Bz, bc2(0.25f), __fmul2_rn(Tz, bc2(0.75f))));
         quad_pair<false, kPairTap>(tp, lane_x(s2), lane_y(s2), mnR, mnG, mnB, mxR, mxG, mxB, oA2, oB2);
-        if (okA2) *reinterpret_cast<uint2*>(orow2) = oA2;
-        if (okB2) *reinterpret_cast<uint2*>(orow2 + 8) = oB2;
+        ST::put(orow2, oA2, okA2);
+        ST::put(orow2 + ST::kBpp, oB2, okB2);
       }
       if (rowB) {
         const Shape2 s2 = pixel_shape2(__ffma2_rn(Bx, bc2(0.75f), __fmul2_rn(Tx, bc2(0.25f))),
                                        __ffma2_rn(By, bc2(0.75f), __fmul2_rn(Ty, bc2(0.25f))),
                                        __ffma2_rn(Bz, bc2(0.75f), __fmul2_rn(Tz, bc2(0.25f))));
         quad_pair<true, kPairTap>(tp, lane_x(s2), lane_y(s2), mnR, mnG, mnB, mxR, mxG, mxB, oA2, oB2);
-        if (okA2) *reinterpret_cast<uint2*>(orow2 + p.out.pitch) = oA2;
-        if (okB2) *reinterpret_cast<uint2*>(orow2 + p.out.pitch + 8) = oB2;
+        ST::put(orow2 + p.out.pitch, oA2, okA2);
+        ST::put(orow2 + p.out.pitch + ST::kBpp, oB2, okB2);
       }
       return;
     }
@@ -636,6 +657,103 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
   }
 }
 
+// ---- 2x EASU for the UNORM formats the sample renders into (experimental, FSR1_UNORM_TILED=1) --------------------------
+// Same phases as easu_h_quad2x_kernel.  The TMA box holds 4-byte texels (origin rounded down to 4 texels = 16 bytes, so
+// the box is 40 wide); one pass decodes it (c / (2^n - 1), fp32) into the half tile the tap loop reads and into the
+// fp32 luma plane; the epilogue re-encodes in the half domain (StoreUnorm).  Against quantise(oracle(dequantise(in))) the
+// stored codes differ by at most one (half tile + half taps), like the default arithmetic of the direct kernels.
+constexpr int kUBW = kQBW + 4;
+template <int NW> struct __align__(128) QuadSmemU {
+  uint32_t stage[2][((kUBW * QuadCfg<NW>::kBH * 4 + 127) / 128) * 128 / 4];
+  uint2 tile[QuadCfg<NW>::kPad];
+  float4 S[kQSW * QuadCfg<NW>::kSH];
+  float L[QuadCfg<NW>::kElems];
+  uint64_t bar[2];
+};
+
+template <int kBits> __device__ __forceinline__ float3 unorm_decode(uint32_t u) {
+  if (kBits == 8) {
+    const float k = 1.0f / 255.0f;
+    return make_float3((float)(u & 255u) * k, (float)((u >> 8) & 255u) * k, (float)((u >> 16) & 255u) * k);
+  }
+  const float k = 1.0f / 1023.0f;
+  return make_float3((float)(u & 1023u) * k, (float)((u >> 10) & 1023u) * k, (float)((u >> 20) & 1023u) * k);
+}
+
+template <int NW, int MINB, int kBits>
+__global__ void __launch_bounds__(NW * 32, MINB)
+easu_u_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap, const int tiles_x, const int n_tiles,
+                     const int mbase) {
+  using C = QuadCfg<NW>;
+  constexpr int NT = NW * 32;
+  constexpr uint32_t kBoxBytes = kUBW * C::kBH * 4u;
+  __shared__ QuadSmemU<NW> sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int t = blockIdx.x;
+  int tx = t % tiles_x, ty = t / tiles_x;
+  const int step_x = (int)gridDim.x % tiles_x, step_y = (int)gridDim.x / tiles_x;
+  // tile (tx, ty): half tile origin gx0 = 32 tx - 2 (as in the half kernel); the staging box starts 2 texels further left
+  if (tid == 0 && t < n_tiles) {
+    mbar_expect_tx(&sm.bar[0], kBoxBytes);
+    tma_load_2d(sm.stage[0], &tmap, tx * kQCX - 4, mbase + ty * C::kCY - 1 - p.in.row0, &sm.bar[0]);
+  }
+  for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
+    const int b = it & 1;
+    int txn = tx + step_x, tyn = ty + step_y;
+    if (txn >= tiles_x) { txn -= tiles_x; tyn++; }
+    if (tid == 0 && t + (int)gridDim.x < n_tiles) {
+      fence_proxy_async();
+      mbar_expect_tx(&sm.bar[b ^ 1], kBoxBytes);
+      tma_load_2d(sm.stage[b ^ 1], &tmap, txn * kQCX - 4, mbase + tyn * C::kCY - 1 - p.in.row0, &sm.bar[b ^ 1]);
+    }
+    const int gx0 = tx * kQCX - 2, gy0 = mbase + ty * C::kCY - 1;
+    tx = txn;
+    ty = tyn;
+    uint32_t* stage = sm.stage[b];
+    mbar_wait(&sm.bar[b], (it >> 1) & 1);
+    if (gx0 < 0 || gy0 < 0 || gx0 + kQBW > p.in.w || gy0 + C::kBH > p.in.h) {  // zero fill -> clamp-to-edge, on the raw texels
+      for (int j = warp; j < C::kBH; j += NW) {
+        const int cy = clampi(gy0 + j, 0, p.in.h - 1) - gy0;
+        for (int i = lane; i < kQBW; i += 32) {
+          const int cx = clampi(gx0 + i, 0, p.in.w - 1) - gx0;
+          if ((cx != i || cy != j) && cx >= 0 && cx < kQBW && cy >= 0 && cy < C::kBH) stage[j * kUBW + 2 + i] = stage[cy * kUBW + 2 + cx];
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();
+    }
+    for (int i = tid; i < C::kElems; i += NT) {  // decode: half tile for the taps, fp32 luma for the analysis
+      const int j = i / kQBW, c = i - j * kQBW;
+      const float3 v = unorm_decode<kBits>(stage[j * kUBW + 2 + c]);
+      sm.tile[i] = make_uint2(h22u(__floats2half2_rn(v.x, v.y)), h22u(__floats2half2_rn(v.z, 1.0f)));
+      sm.L[i] = fmaf(v.z, 0.5f, fmaf(v.x, 0.5f, v.y));
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kQSW * C::kSH; idx += NT) {
+      const int j = idx / kQSW, i = idx - j * kQSW;
+      const float* c = sm.L + (j + 1) * kQBW + (i + 1);
+      sm.S[idx] = texel_terms(c[-kQBW], c[-1], c[0], c[1], c[kQBW]);
+    }
+    __syncthreads();
+    const bool inside = 2 * (gx0 + 1) + 1 >= 0 && 2 * (gx0 + 32) + 2 < p.out.w && 2 * (gy0 + 1) + 1 >= p.y0 &&
+                        2 * (gy0 + C::kCY) + 2 < p.y1;
+    if (inside) {
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) quad_cell<3, true, StoreUnorm<kBits>>(p, sm.tile, sm.S, gx0, gy0, lane, warp + q * NW);
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) quad_cell<3, false, StoreUnorm<kBits>>(p, sm.tile, sm.S, gx0, gy0, lane, warp + q * NW);
+    }
+    __syncthreads();  // stage, tile, L and S are free again
+  }
+}
+
 // ---- warp-specialised variant: one producer warp prepares tile i+1 (TMA wait, clamp fix-up, luma, terms) while
 // NWC consumer warps run phase 3 of tile i.  No CTA-wide barrier in the steady state: the hand-offs are mbarriers
 // (ready[b]: producer -> consumers, free_[b]: consumers -> producer), tile/L/S are all double-buffered.
@@ -756,6 +874,38 @@ static int max_footprint(int n_out, int first, int tile, float scale, float offs
     if (span > best) best = span;
   }
   return best;
+}
+
+// UNORM images, exactly 2x (experimental: FSR1_UNORM_TILED=1; otherwise the caller uses the direct kernels)
+cudaError_t launch_easu_u_tiled(const EasuParams& p, int format, cudaStream_t s, const char** name) {
+  static const int enabled = env_knob("FSR1_UNORM_TILED", 0);  // 1: R8G8B8A8 only, 2: also R10G10B10A2 (coarser than its codes)
+  if (!(enabled >= 1 && format == 3) && !(enabled >= 2 && format == 4)) return cudaErrorNotSupported;
+  if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15)) return cudaErrorNotSupported;  // TMA
+  if (!(p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f)) return cudaErrorNotSupported;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return cudaErrorNotSupported;
+  constexpr int NW = 4, CY = 2 * NW;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)p.in.w, (cuuint64_t)p.in.rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.in.pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)kUBW, (cuuint32_t)(CY + 3)};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p.in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorNotSupported;
+  const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
+  const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
+  const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
+  const int tiles_y = (m_last - m_first + 1 + CY - 1) / CY, n_tiles = tiles_x * tiles_y;
+  const int grid = n_tiles < 6 * sm_count() ? n_tiles : 6 * sm_count();
+  if (format == 3) {
+    easu_u_quad2x_kernel<NW, 6, 8><<<grid, NW * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+    *name = "easu_u8_quad2x<4w,6/sm,tma2>";
+  } else {
+    easu_u_quad2x_kernel<NW, 6, 10><<<grid, NW * 32, 0, s>>>(p, tmap, tiles_x, n_tiles, m_first);
+    *name = "easu_u10_quad2x<4w,6/sm,tma2>";
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name) {

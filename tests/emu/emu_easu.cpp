@@ -161,3 +161,55 @@ extern "C" int emu_rcas_h_packed(const void* in, void* out, int w, int h, long l
   return 0;
 }
 
+// easu_u_quad2x_kernel: 2x EASU on R8G8B8A8_UNORM (bits = 8) / R10G10B10A2_UNORM (bits = 10) images, 4 bytes per texel.
+extern "C" int emu_easu_u_quad2x(int bits, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
+                                 long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
+  EasuParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
+  p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
+  memcpy(&p.c0x, &con[0], 4); memcpy(&p.c0y, &con[1], 4); memcpy(&p.c0z, &con[2], 4); memcpy(&p.c0w, &con[3], 4);
+  p.y0 = y0; p.y1 = y1;
+  if (!(p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) || (bits != 8 && bits != 10)) return -1;
+  constexpr int NW = 4, CY = 2 * NW;
+  const int k_first = -1, k_last = cell_of(ow - 1, 0.5f, -0.25f);
+  const int m_first = cell_of(y0, 0.5f, -0.25f), m_last = cell_of(y1 - 1, 0.5f, -0.25f);
+  const int tiles_x = (k_last - k_first + 1 + kQCX - 1) / kQCX;
+  const int tiles_y = (m_last - m_first + 1 + CY - 1) / CY, n_tiles = tiles_x * tiles_y;
+  const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+  CUtensorMap tmap{(const unsigned char*)in, iw, ih, in_pitch, kUBW, CY + 3, 4};
+  if (bits == 8) run_grid(easu_u_quad2x_kernel<4, 6, 8>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first);
+  else run_grid(easu_u_quad2x_kernel<4, 6, 10>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first);
+  return 0;
+}
+
+// rcas_u_packed_kernel: RCAS on UNORM images (bits = 8 or 10), 4 bytes per texel.
+extern "C" int emu_rcas_u_packed(int bits, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                                 const uint32_t* con, int clamp, int y0, int y1) {
+  if (bits != 8 && bits != 10) return -1;
+  RcasParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
+  p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
+  memcpy(&p.sharp, &con[0], 4);
+  p.sharp_h2 = con[1];
+  p.y0 = y0; p.y1 = y1; p.clamp = clamp; p.options = 0;
+  constexpr int NWARP = 4, threads = 32 * NWARP;
+  const int gx = (w + kSpan - 1) / kSpan, gy = (y1 - y0 + 15) / 16;
+  for (int by = 0; by < gy; by++)
+    for (int bx = 0; bx < gx; bx++) {
+      for (int i = 0; i < NWARP; i++) pthread_barrier_init(&g_warp_barrier[i], nullptr, 32);
+      std::vector<std::thread> ts;
+      for (int t = 0; t < threads; t++)
+        ts.emplace_back([=, &p]() {
+          threadIdx = uint3{(unsigned)t, 0, 0};
+          blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
+          gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
+          blockDim.x = (unsigned)threads;
+          if (bits == 8) { if (clamp) rcas_u_packed_kernel<true, 8>(p); else rcas_u_packed_kernel<false, 8>(p); }
+          else { if (clamp) rcas_u_packed_kernel<true, 10>(p); else rcas_u_packed_kernel<false, 10>(p); }
+        });
+      for (auto& th : ts) th.join();
+      for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
+    }
+  return 0;
+}
+

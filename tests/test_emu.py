@@ -136,3 +136,77 @@ def test_emulated_rcas_kernel_within_fp16_tolerance(size, clamp):
     assert np.array_equal(part[y0:y1].view(np.uint16), full[y0:y1].view(np.uint16))
     assert not part[:y0].view(np.uint16).any() and not part[y1:].view(np.uint16).any()
 
+
+def _quantise(x, bits):
+    s = np.float32((1 << bits) - 1)
+    return (np.clip(x, 0.0, 1.0).astype(np.float32) * s + np.float32(0.5)).astype(np.uint32)
+
+
+def _pack_unorm(q, bits):
+    if bits == 8:
+        return (q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | (q[..., 3] << 24)).astype(np.uint32)
+    return (q[..., 0] | (q[..., 1] << 10) | (q[..., 2] << 20) | (q[..., 3] << 30)).astype(np.uint32)
+
+
+def _unpack_unorm(w, bits):
+    if bits == 8:
+        return np.stack([w & 255, (w >> 8) & 255, (w >> 16) & 255, w >> 24], axis=-1)
+    return np.stack([w & 1023, (w >> 10) & 1023, (w >> 20) & 1023, w >> 30], axis=-1)
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+@pytest.mark.parametrize("size", [(64, 36), (70, 23), (33, 17)])
+def test_emulated_unorm_2x_easu_within_one_code(bits, size):
+    """easu_u_quad2x_kernel (prepared, FSR1_UNORM_TILED=1): TMA box of 4-byte texels, decode to the half tile + fp32 luma,
+    half-domain re-encode.  Against quantise(oracle(dequantise(input))): at most one code value off, and rarely."""
+    iw, ih = size
+    ow, oh = 2 * iw, 2 * ih
+    rng = np.random.default_rng(3)
+    top = (1 << bits) - 1
+    for kind in ("noise", "smooth"):
+        if kind == "noise":
+            raw = rng.integers(0, top + 1, size=(ih, iw, 4), dtype=np.uint32)
+        else:
+            raw = _quantise(F.structured(iw, ih, 12), bits)
+        raw[..., 3] = rng.integers(0, 4 if bits == 10 else 256, size=(ih, iw))
+        fin = (raw.astype(np.float32) / np.float32(top)).astype(np.float32)
+        want = _quantise(ol.easu(fin, ow, oh)[..., :3], bits)
+        src = np.ascontiguousarray(_pack_unorm(raw, bits))
+        out = np.zeros((oh, ow), np.uint32)
+        con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
+        rc = emu_lib().emu_easu_u_quad2x(bits, ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
+                                         ctypes.c_void_p(out.ctypes.data), ow, oh, ctypes.c_longlong(out.strides[0]), con, 0, oh, 3)
+        assert rc == 0
+        got = _unpack_unorm(out, bits)
+        diff = np.abs(got[..., :3].astype(np.int64) - want.astype(np.int64))
+        assert diff.max() <= (1 if bits == 8 else 3), (kind, int(diff.max()))     # 10-bit codes are finer than half's 11-bit mantissa
+        assert (diff > 0).mean() < (0.10 if bits == 8 else 0.6), (kind, float((diff > 0).mean()))
+        assert (got[..., 3] == (255 if bits == 8 else 3)).all()
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+@pytest.mark.parametrize("clamp", [False, True])
+def test_emulated_unorm_rcas_within_one_code(bits, clamp):
+    """rcas_u_packed_kernel (prepared, FSR1_UNORM_TILED=1): decode two 4-byte pixels per lane, the half2 RCAS arithmetic of the
+    production kernel, saturate, re-encode.  Against quantise(oracle(dequantise(input)))."""
+    rng = np.random.default_rng(4)
+    top = (1 << bits) - 1
+    for (w, h) in ((128, 40), (61, 19), (6, 5)):
+        for kind in ("noise", "smooth"):
+            raw = rng.integers(0, top + 1, size=(h, w, 4), dtype=np.uint32) if kind == "noise" else _quantise(F.structured(w, h, 12), bits)
+            raw[..., 3] = 3 if bits == 10 else 255
+            fin = (raw.astype(np.float32) / np.float32(top)).astype(np.float32)
+            src = np.ascontiguousarray(_pack_unorm(raw, bits))
+            for sharp in (0.0, 0.25):
+                want = _quantise(ol.rcas(fin, ol.rcas_con(sharp), clamp)[..., :3], bits)
+                out = np.zeros((h, w), np.uint32)
+                con = (ctypes.c_uint32 * 4)(*ol.rcas_con(sharp))
+                rc = emu_lib().emu_rcas_u_packed(bits, ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(out.ctypes.data), w, h,
+                                                 ctypes.c_longlong(src.strides[0]), ctypes.c_longlong(out.strides[0]), con,
+                                                 1 if clamp else 0, 0, h)
+                assert rc == 0
+                got = _unpack_unorm(out, bits)
+                diff = np.abs(got[..., :3].astype(np.int64) - want.astype(np.int64))
+                assert diff.max() <= (1 if bits == 8 else 4), (w, h, kind, sharp, int(diff.max()))
+                assert (got[..., 3] == (255 if bits == 8 else 3)).all()
+

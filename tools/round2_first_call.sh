@@ -19,3 +19,8 @@ for v in 0 1; do
   FSR1_EASU_PAIRS_VARIANT=$v timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "fp16_kernels or golden or end_to_end or slabs or dynamic" 2>&1 | tail -1
   for s in 1.5x 1.3x; do FSR1_EASU_PAIRS_VARIANT=$v timeout 90 python tools/variant_time.py $s 2>&1 | tail -1; done
 done
+for v in 0 1; do
+  echo "== FSR1_UNORM_TILED=$v (RGBA8 images: 0 = direct kernels, 1 = TMA-tiled EASU + packed RCAS)"
+  FSR1_UNORM_TILED=$v timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -k unorm 2>&1 | tail -1
+  FSR1_UNORM_TILED=$v timeout 120 python tools/unorm_time.py 2>&1 | tail -2
+done
