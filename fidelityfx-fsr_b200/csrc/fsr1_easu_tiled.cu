@@ -508,7 +508,7 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
     const __half2 mxBA = __hmax2(__hmax2(u2h2(tp[1][1].y), u2h2(tp[1][2].y)), __hmax2(u2h2(tp[2][1].y), u2h2(tp[2][2].y)));
     const __half2 mnR = __low2half2(mnRG), mnG = __high2half2(mnRG), mnB = __low2half2(mnBA);
     const __half2 mxR = __low2half2(mxRG), mxG = __high2half2(mxRG), mxB = __low2half2(mxBA);
-    if constexpr (kTap >= 2) {
+    if constexpr (kTap == 2 || kTap == 3) {
       constexpr int kPairTap = kTap == 2 ? 1 : 3;
       // packed pair (A: px=.25, B: px=.75): T = top texel row f,g blended horizontally, Bm = bottom texel row j,k
       const float2 wF = mk2(0.75f, 0.25f), wG = mk2(0.25f, 0.75f);
@@ -544,19 +544,19 @@ __device__ __forceinline__ void quad_cell(const EasuParams& p, const uint2* __re
     const float3 b25 = make_float3(fmaf(k.x, gx, j.x * fx), fmaf(k.y, gx, j.y * fx), fmaf(k.z, gx, j.z * fx));
     const float3 b75 = make_float3(fmaf(k.x, fx, j.x * gx), fmaf(k.y, fx, j.y * gx), fmaf(k.z, fx, j.z * gx));
     unsigned char* orow = p.out.base + (long long)(oyT - p.out.row0) * p.out.pitch + (long long)oxA * 8;
-    const bool okA = oxA >= 0, okB = oxA + 1 < p.out.w;
+    const bool okA = kFast || oxA >= 0, okB = kFast || oxA + 1 < p.out.w;
     uint2 oA, oB;
     if (rowT) {
       const Shape sA = pixel_shape(fmaf(b25.x, gx, t25.x * fx), fmaf(b25.y, gx, t25.y * fx), fmaf(b25.z, gx, t25.z * fx));
       const Shape sB = pixel_shape(fmaf(b75.x, gx, t75.x * fx), fmaf(b75.y, gx, t75.y * fx), fmaf(b75.z, gx, t75.z * fx));
-      quad_pair<false, (kTap >= 2 ? 1 : kTap)>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<false, (kTap == 4 ? 3 : (kTap >= 2 ? 1 : kTap))>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + 8) = oB;
     }
     if (rowB) {
       const Shape sA = pixel_shape(fmaf(b25.x, fx, t25.x * gx), fmaf(b25.y, fx, t25.y * gx), fmaf(b25.z, fx, t25.z * gx));
       const Shape sB = pixel_shape(fmaf(b75.x, fx, t75.x * gx), fmaf(b75.y, fx, t75.y * gx), fmaf(b75.z, fx, t75.z * gx));
-      quad_pair<true, (kTap >= 2 ? 1 : kTap)>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
+      quad_pair<true, (kTap == 4 ? 3 : (kTap >= 2 ? 1 : kTap))>(tp, sA, sB, mnR, mnG, mnB, mxR, mxG, mxB, oA, oB);
       if (okA) *reinterpret_cast<uint2*>(orow + p.out.pitch) = oA;
       if (okB) *reinterpret_cast<uint2*>(orow + p.out.pitch + 8) = oB;
     }
@@ -918,7 +918,8 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
   if (p.c0x == 0.5f && p.c0y == 0.5f && p.c0z == -0.25f && p.c0w == -0.25f) {  // exactly 2x
     // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
     // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance),
-    // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp), 9 (8 + predicate-free path for interior tiles)
+    // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp), 9 (8 + predicate-free path for interior tiles + incremental tile coordinates),
+    // 10 (the default's scalar fp32 analysis with 9's integer clamp, interior path and incremental coordinates)
     static const int variant = env_knob("FSR1_EASU_QUAD_VARIANT", 6);
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
@@ -951,6 +952,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     if (variant == 7) return launch(easu_h_quad2x_kernel<4, 6, 2>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape>");  // experimental
     if (variant == 8) return launch(easu_h_quad2x_kernel<4, 6, 3>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp>");  // experimental
     if (variant == 9) return launch(easu_h_quad2x_kernel<4, 6, 3, true>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp,interior>");  // experimental
+    if (variant == 10) return launch(easu_h_quad2x_kernel<4, 6, 4, true>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,iclamp,interior>");  // experimental
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6, 1>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");

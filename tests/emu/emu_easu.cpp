@@ -55,7 +55,7 @@ static void run_grid(Kernel kernel, int grid, int threads, const EasuParams& p, 
   }
 }
 
-// variant: the FSR1_EASU_QUAD_VARIANT numbering of launch_easu_h_tiled (2 plain, 6 default, 7, 8, 9).
+// variant: the FSR1_EASU_QUAD_VARIANT numbering of launch_easu_h_tiled (2 plain, 6 default, 7, 8, 9, 10).
 // Images are RGBA16F, whole frames (row0 = 0).  Returns 0, or -1 for an unknown variant / not exactly 2x.
 extern "C" int emu_easu_h_quad2x(int variant, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
                                  long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
@@ -78,6 +78,7 @@ extern "C" int emu_easu_h_quad2x(int variant, const void* in, int iw, int ih, lo
     case 7: run_grid(easu_h_quad2x_kernel<4, 6, 2, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
     case 8: run_grid(easu_h_quad2x_kernel<4, 6, 3, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
     case 9: run_grid(easu_h_quad2x_kernel<4, 6, 3, true>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
+    case 10: run_grid(easu_h_quad2x_kernel<4, 6, 4, true>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
     default: return -1;
   }
   return 0;

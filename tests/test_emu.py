@@ -5,7 +5,7 @@ What it proves on CPU, for the 2x EASU kernel family:
   * the production variant (FSR1_EASU_QUAD_VARIANT=6) stays within the fp16 tolerance of the fp32 oracle — tiling,
     clamp-to-edge fix-up, persistent tile loop, row ranges and image borders included;
   * the variants prepared for measurement (7: f32x2-packed per-pixel analysis, 8: integer distance clamp, 9: predicate-free
-    interior path + incremental tile coordinates) produce the SAME BITS as the production variant.
+    interior path + incremental tile coordinates, 10: 9 with the default's scalar fp32 analysis) produce the SAME BITS as the production variant.
 The GPU remains the authority on the hardware (tests/test_gpu_parity.py); this is a second, cheaper net."""
 import ctypes
 import os
@@ -64,7 +64,7 @@ def test_emulated_row_range_only_touches_its_rows():
     assert not part[:19].view(np.uint16).any() and not part[53:].view(np.uint16).any()
 
 
-@pytest.mark.parametrize("variant", [7, 8, 9])
+@pytest.mark.parametrize("variant", [7, 8, 9, 10])
 def test_prepared_variants_are_bit_identical_to_production(variant):
     for (iw, ih) in ((64, 36), (70, 23), (33, 17), (99, 40)):   # sizes whose FsrEasuCon scale is exactly 0.5 (97 is not)
         for gen in (F.uniform, F.structured):
