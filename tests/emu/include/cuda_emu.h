@@ -82,6 +82,7 @@ inline __half2 __highs2half2(__half2 a, __half2 b) { return mkh2(a.y, b.y); }
 // products of two halves are exact in double, and so is the sum with a third: a single rounding to half at the end
 inline __half hfma1(__half a, __half b, __half c) { return d2h((double)h2f(a) * (double)h2f(b) + (double)h2f(c)); }
 inline __half2 __hfma2(__half2 a, __half2 b, __half2 c) { return mkh2(hfma1(a.x, b.x, c.x), hfma1(a.y, b.y, c.y)); }
+inline __half2 __hfma2_relu(__half2 a, __half2 b, __half2 c) { __half2 r = mkh2(hfma1(a.x, b.x, c.x), hfma1(a.y, b.y, c.y)); if (!(h2f(r.x) > 0.0f)) r.x.b = 0; if (!(h2f(r.y) > 0.0f)) r.y.b = 0; return r; }
 inline __half2 __hmul2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) * h2f(b.x)), d2h((double)h2f(a.y) * h2f(b.y))); }
 inline __half2 __hadd2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) + h2f(b.x)), d2h((double)h2f(a.y) + h2f(b.y))); }
 inline __half2 __hsub2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) - h2f(b.x)), d2h((double)h2f(a.y) - h2f(b.y))); }
