@@ -27,6 +27,7 @@ unsigned char* fsr1_emu_dynamic_smem() { return g_dynamic_smem; }
 
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_easu_tiled.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_packed.cu"
+#include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_f32.cu"
 
 using namespace fsr1;
 
@@ -210,6 +211,35 @@ extern "C" int emu_rcas_u_packed(int bits, const void* in, void* out, int w, int
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
+    }
+  return 0;
+}
+
+// rcas_f32_packed_kernel<kApprox>: RCAS on RGBA32F images (variant 1 = MUFU reciprocal, FSR1_RCAS_F32_VARIANT=1).
+extern "C" int emu_rcas_f32_packed(int variant, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                                   const uint32_t* con, int clamp, int y0, int y1) {
+  RcasParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
+  p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
+  memcpy(&p.sharp, &con[0], 4);
+  p.sharp_h2 = con[1];
+  p.y0 = y0; p.y1 = y1; p.clamp = clamp; p.options = 0;
+  const int threads = 32 * kFWarps;
+  const int gx = (w + kFSpan - 1) / kFSpan, gy = (y1 - y0 + kFWarps * kFRows - 1) / (kFWarps * kFRows);
+  for (int by = 0; by < gy; by++)
+    for (int bx = 0; bx < gx; bx++) {
+      for (int i = 0; i < kFWarps; i++) pthread_barrier_init(&g_warp_barrier[i], nullptr, 32);
+      std::vector<std::thread> ts;
+      for (int t = 0; t < threads; t++)
+        ts.emplace_back([=, &p]() {
+          threadIdx = uint3{(unsigned)t, 0, 0};
+          blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
+          gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
+          blockDim.x = (unsigned)threads;
+          if (variant == 1) rcas_f32_packed_kernel<true>(p); else rcas_f32_packed_kernel<false>(p);
+        });
+      for (auto& th : ts) th.join();
+      for (int i = 0; i < kFWarps; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
     }
   return 0;
 }

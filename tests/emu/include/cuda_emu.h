@@ -113,6 +113,8 @@ inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned delta) {
   const int lane = (int)(threadIdx.x & 31);
   return fsr1_emu_shfl(v, lane + (int)delta < 32 ? lane + (int)delta : -1);
 }
+inline float __shfl_up_sync(unsigned m, float v, unsigned delta) { return __uint_as_float(__shfl_up_sync(m, __float_as_uint(v), delta)); }
+inline float __shfl_down_sync(unsigned m, float v, unsigned delta) { return __uint_as_float(__shfl_down_sync(m, __float_as_uint(v), delta)); }
 
 // ---- emulated TMA descriptor + mbarrier (see fsr1_emu_ptx.h) ----------------------------------------------
 struct CUtensorMap {

@@ -210,3 +210,22 @@ def test_emulated_unorm_rcas_within_one_code(bits, clamp):
                 assert diff.max() <= (1 if bits == 8 else 4), (w, h, kind, sharp, int(diff.max()))
                 assert (got[..., 3] == (255 if bits == 8 else 3)).all()
 
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emulated_fp32_rcas_within_1e5(variant):
+    """rcas_f32_packed_kernel (variant 1 = FSR1_RCAS_F32_VARIANT=1, MUFU reciprocal, prepared): the fp32 fast path is held to
+    1e-5 of the oracle (contraction reorders roundings; bit-exactness is FSR1_FLAG_EXACT's job)."""
+    for (w, h) in ((128, 40), (61, 19), (6, 5)):
+        for gen in (F.uniform, F.structured):
+            src = np.ascontiguousarray(gen(w, h, 9))
+            for clamp in (False, True):
+                for sharp in (0.0, 0.25, 2.0):
+                    con = (ctypes.c_uint32 * 4)(*ol.rcas_con(sharp))
+                    out = np.zeros_like(src)
+                    rc = emu_lib().emu_rcas_f32_packed(variant, ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(out.ctypes.data), w, h,
+                                                       ctypes.c_longlong(src.strides[0]), ctypes.c_longlong(out.strides[0]), con,
+                                                       1 if clamp else 0, 0, h)
+                    assert rc == 0
+                    want = ol.rcas(src, ol.rcas_con(sharp), clamp)
+                    assert np.abs(out - want)[..., :3].max() <= 1e-5
+

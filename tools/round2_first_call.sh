@@ -24,3 +24,8 @@ for v in 0 1; do
   FSR1_UNORM_TILED=$v timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -k unorm 2>&1 | tail -1
   FSR1_UNORM_TILED=$v timeout 120 python tools/unorm_time.py 2>&1 | tail -2
 done
+for v in 0 1; do
+  echo "== FSR1_RCAS_F32_VARIANT=$v (RGBA32F RCAS: 1 = MUFU reciprocal instead of IEEE __frcp_rn, -25 % instructions)"
+  FSR1_RCAS_F32_VARIANT=$v timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "fp32_default or flat" 2>&1 | tail -1
+  FSR1_RCAS_F32_VARIANT=$v timeout 120 python bench.py --workload 1080p-4k-fp32 --no-cpu --no-pipeline --steps 100 --warmup 10 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:(round(v['us'],1)) for k,v in d['kernels'].items()})"
+done
