@@ -919,7 +919,8 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     // development knob: FSR1_EASU_QUAD_VARIANT = 0 (8 warps x2), 1 (8 warps x3), 2 (4 warps x6, plain tap form),
     // 3/4 (warp-specialised), 5 (4 warps x7), 6 = default (4 warps x6, factored tap distance),
     // 7 (experimental, unmeasured: as 6 with the per-pixel fp32 analysis packed in f32x2), 8 (7 + integer distance clamp), 9 (8 + predicate-free path for interior tiles + incremental tile coordinates),
-    // 10 (the default's scalar fp32 analysis with 9's integer clamp, interior path and incremental coordinates)
+    // 10 (the default's scalar fp32 analysis with 9's integer clamp, interior path and incremental coordinates),
+    // 12 (9 at 7 CTAs per SM: variant 9 needs 72 registers, which is exactly what 7 x 128 threads allow)
     static const int variant = env_knob("FSR1_EASU_QUAD_VARIANT", 6);
     const int k_first = -1, k_last = host_fp(p.out.w - 1, 0.5f, -0.25f);
     const int m_first = host_fp(p.y0, 0.5f, -0.25f), m_last = host_fp(p.y1 - 1, 0.5f, -0.25f);
@@ -953,6 +954,7 @@ cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char*
     if (variant == 8) return launch(easu_h_quad2x_kernel<4, 6, 3>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp>");  // experimental
     if (variant == 9) return launch(easu_h_quad2x_kernel<4, 6, 3, true>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,f32x2shape,iclamp,interior>");  // experimental
     if (variant == 10) return launch(easu_h_quad2x_kernel<4, 6, 4, true>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2,iclamp,interior>");  // experimental
+    if (variant == 12) return launch(easu_h_quad2x_kernel<4, 7, 3, true>, 4, 7, "easu_h_quad2x<4w,7/sm,tma2,f32x2shape,iclamp,interior>");  // experimental
     if (variant == 0) return launch(easu_h_quad2x_kernel<8, 2>, 8, 2, "easu_h_quad2x<8w,2/sm,tma2>");
     if (variant == 1) return launch(easu_h_quad2x_kernel<8, 3>, 8, 3, "easu_h_quad2x<8w,3/sm,tma2>");
     return launch(easu_h_quad2x_kernel<4, 6, 1>, 4, 6, "easu_h_quad2x<4w,6/sm,tma2>");

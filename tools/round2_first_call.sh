@@ -3,8 +3,8 @@
 #   gpurun --timeout 600 -- 'bash tools/round2_first_call.sh > gpurun_out/round2_first.log 2>&1; cat gpurun_out/round2_first.log'
 mkdir -p gpurun_out
 timeout 60 tools/bin/ubench_pipes | tee gpurun_out/ubench_pipes_r2.txt          # tick calibration + VIMNMX / FFMA2 mixes
-for v in 6 7 8 9 10; do
-  echo "== FSR1_EASU_QUAD_VARIANT=$v  (6 = default; 7 = f32x2-packed per-pixel analysis; 8 = 7 + integer distance clamp; 9 = 8 + predicate-free interior tiles + incremental tile coordinates; 10 = 9 with scalar fp32 analysis)"
+for v in 6 7 8 9 10 12; do
+  echo "== FSR1_EASU_QUAD_VARIANT=$v  (6 = default; 7 = f32x2-packed per-pixel analysis; 8 = 7 + integer distance clamp; 9 = 8 + predicate-free interior tiles + incremental tile coordinates; 10 = 9 with scalar fp32 analysis; 12 = 9 at 7 CTAs per SM)"
   FSR1_EASU_QUAD_VARIANT=$v timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q \
       -k "fp16_kernels or golden or end_to_end or full_size or slabs or pipeline or flat" 2>&1 | tail -2
   FSR1_EASU_QUAD_VARIANT=$v timeout 90 python tools/variant_time.py 2x 2>&1 | tail -2
