@@ -265,7 +265,7 @@ def run_ours(args, rank, world, local_rank):
         elif args.no_overlap:
             def step(i):
                 ups[i % RING].upscale()
-        elif args.halo_depth > 1 or args.pipeline_sharded:
+        elif args.halo_depth > 1 or args.pipeline_sharded or args.halo_batch > 1:
             # EXPERIMENTAL (not the default): halo exchange `halo_depth` frames ahead (more slack against rank-to-rank
             # jitter than the one-frame prefetch below) and, with --pipeline-sharded, RCAS of frame i on a second
             # stream while EASU of frame i+1 runs (api.FramePipeline over the slab windows), as at N=1
@@ -290,15 +290,33 @@ def run_ours(args, rank, world, local_rank):
                 with torch.cuda.stream(comm):
                     ups[k]._exchange()
                     ready[k].record(comm)
-            for j in range(depth):
-                prefetch(j)
+            batch = max(1, min(args.halo_batch, RING // 2))
+
+            def prefetch_group(g):               # --halo-batch: the halos of `batch` consecutive frames in ONE NCCL group
+                slots = [(g * batch + t) % RING for t in range(batch)]
+                for k in slots:
+                    if used[k]:
+                        comm.wait_event(done[k])
+                with torch.cuda.stream(comm):
+                    F.ShardedUpscaler.exchange_many([ups[k] for k in slots])
+                    for k in slots:
+                        ready[k].record(comm)
+            if batch > 1:
+                prefetch_group(0)
+            else:
+                for j in range(depth):
+                    prefetch(j)
             frame = [0]
 
             def step(_):
                 i = frame[0]
                 frame[0] += 1
                 k = i % RING
-                prefetch(i + depth)
+                if batch > 1:
+                    if i % batch == 0:
+                        prefetch_group(i // batch + 1)
+                else:
+                    prefetch(i + depth)
                 if pipe is not None:
                     pipe.stream_easu.wait_event(ready[k])
                     pipe.submit(k)
@@ -446,8 +464,9 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * ih + 2 * ow * oh) * bpp / 1e6),
                        "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step, %s" % (
                            world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else (
-                               "EXPERIMENTAL: halo exchange %d frames ahead%s" % (args.halo_depth, ", RCAS/EASU of consecutive frames on two streams" if args.pipeline_sharded else "")
-                               if (args.halo_depth > 1 or args.pipeline_sharded) else "halo exchange of frame i+1 overlapped with frame i on a second stream")))},
+                               "EXPERIMENTAL: halo exchange %s%s" % ("of %d frames per NCCL group" % args.halo_batch if args.halo_batch > 1 else "%d frames ahead" % args.halo_depth,
+                                                                      ", RCAS/EASU of consecutive frames on two streams" if args.pipeline_sharded else "")
+                               if (args.halo_depth > 1 or args.pipeline_sharded or args.halo_batch > 1) else "halo exchange of frame i+1 overlapped with frame i on a second stream")))},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1:
@@ -502,6 +521,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--halo-depth", type=int, default=1, help="multi-GPU (experimental): exchange halos this many frames ahead (default 1 = the measured configuration)")
+    ap.add_argument("--halo-batch", type=int, default=1, help="multi-GPU (experimental): exchange the halos of this many consecutive frames in one NCCL group (<= ring/2)")
     ap.add_argument("--pipeline-sharded", action="store_true", help="multi-GPU (experimental): overlap RCAS of frame i with EASU of frame i+1 on two streams, as at N=1")
     ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")

@@ -7,7 +7,7 @@ include/fsr1_b200.h); this package is the reference-shaped host layer over it.
 """
 from . import _lib  # noqa: F401
 from .frames import structured, to_half, uniform  # noqa: F401
-from .sharded import SlabPlan, exchange_halo  # noqa: F401
+from .sharded import SlabPlan, exchange_halo, exchange_halo_many  # noqa: F401
 
 
 def __getattr__(name):  # torch-dependent parts load lazily so geometry/frames work without torch

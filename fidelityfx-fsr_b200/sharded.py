@@ -101,6 +101,30 @@ def exchange_halo(plan, rank, owned, window, dist=None):
     return len(ops)
 
 
+def exchange_halo_many(plan, rank, frames, dist=None):
+    """The halo exchange of SEVERAL frames in ONE batched group (one NCCL launch instead of one per frame: the
+    per-frame cost of the exchange is host/launch latency, not bytes).  `frames` is a list of (owned, window) pairs as
+    for exchange_halo; every rank must pass its frames in the same order.  Returns the number of point-to-point ops."""
+    own0, own1 = plan.owned_in_rows(rank)
+    need0, need1 = plan.needed_in_rows(rank)
+    a, b = max(own0, need0), min(own1, need1)
+    sends, recvs = plan.transfers(rank)
+    if dist is None:
+        import torch.distributed as dist
+    ops = []
+    for owned, window in frames:
+        if b > a and owned[a - own0:a - own0 + 1].data_ptr() != window[a - need0:a - need0 + 1].data_ptr():
+            window[a - need0:b - need0].copy_(owned[a - own0:b - own0])
+        for peer, r0, r1 in sends:
+            ops.append(dist.P2POp(dist.isend, owned[r0 - own0:r1 - own0], peer))
+        for peer, r0, r1 in recvs:
+            ops.append(dist.P2POp(dist.irecv, window[r0 - need0:r1 - need0], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return len(ops)
+
+
 class ShardedUpscaler:
     """One instance per rank (one process per GPU).
 
@@ -168,6 +192,22 @@ class ShardedUpscaler:
         ops += [dist.P2POp(dist.irecv, t, peer) for peer, t in self._recvs]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+    @staticmethod
+    def exchange_many(upscalers):
+        """One batched NCCL group carrying the halos of several frames (each frame = one ShardedUpscaler of the same
+        geometry, e.g. the slots of a ring): amortises the per-exchange launch cost when frames are processed in groups."""
+        import torch.distributed as dist
+        ops = []
+        for u in upscalers:
+            if not hasattr(u, "_sends"):
+                u._build_exchange()
+            ops += [dist.P2POp(dist.isend, t, peer) for peer, t in u._sends]
+            ops += [dist.P2POp(dist.irecv, t, peer) for peer, t in u._recvs]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return len(ops)
 
     def _launch(self, stream=None):
         if self._prepared is None:

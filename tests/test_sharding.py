@@ -80,3 +80,29 @@ def test_halo_exchange_gloo(shape, world, tmp_path):
     want = ol.rcas(ol.easu(frame, ow, oh), ol.rcas_con(0.25), False)
     got = np.concatenate([np.load(os.path.join(str(tmp_path), "slab%d.npy" % r)) for r in range(world)])
     assert np.array_equal(got, want)       # sharded == unsharded, bit for bit
+
+
+def _worker_many(rank, world, port, shape, nframes):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    iw, ih, ow, oh = shape
+    plan = F.SlabPlan(ih, oh, world, ol.easu_con(iw, ih, ow, oh))
+    own0, own1 = plan.owned_in_rows(rank)
+    n0, n1 = plan.needed_in_rows(rank)
+    frames = [F.uniform(iw, ih, 100 + t) for t in range(nframes)]
+    pairs = [(torch.from_numpy(f[own0:own1].copy()), torch.full((n1 - n0, iw, 4), float("nan"))) for f in frames]
+    nops = F.exchange_halo_many(plan, rank, pairs)
+    sends, recvs = plan.transfers(rank)
+    assert nops == nframes * (len(sends) + len(recvs))
+    for f, (_, window) in zip(frames, pairs):
+        assert np.array_equal(window.numpy(), f[n0:n1])           # every frame's halo landed in ITS window
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,world", [((48, 40, 96, 80), 2), ((32, 30, 64, 60), 3)])
+def test_batched_halo_exchange_of_several_frames_gloo(shape, world):
+    """exchange_halo_many: the halos of several frames in one batched group (what bench.py --halo-batch uses on NCCL)."""
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_many, args=(world, port, shape, 3), nprocs=world, join=True)
+

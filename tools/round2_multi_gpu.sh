@@ -4,7 +4,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 port=29520
-for flags in "" "--halo-depth 3" "--pipeline-sharded" "--halo-depth 3 --pipeline-sharded"; do
+for flags in "" "--halo-depth 3" "--halo-batch 4" "--pipeline-sharded" "--halo-batch 4 --pipeline-sharded"; do
   port=$((port + 1))
   echo "== N=$N bench.py $flags"
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $port \
