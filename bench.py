@@ -6,7 +6,9 @@
 One "step" = one synthetic frame through EASU -> RCAS.  Default workload = BASELINE.json configs[1]:
 1920x1080 -> 3840x2160, RGBA16F, sharpness 0.25 stops.  With N > 1 (launched by torchrun, one rank per GPU)
 the frame is N slabs tall (1920 x 1080N -> 3840 x 2160N), sharded by output row slab with the EASU input halo
-exchanged between neighbouring ranks over NCCL every step: per-GPU work is fixed ("weak" scaling).
+moved between neighbouring ranks every step (direct NVLink stores through the C ABI's fsr1_shard_*, or NCCL with --halo nccl):
+per-GPU work is fixed ("weak" scaling).  Every N runs the SAME schedule (fsr1_shard: RCAS of frame i overlaps EASU of frame i+1).
+N > 1 lines carry "parity" (sharded == single GPU bit for bit, both data planes, oracle bands) and "halo" (what the exchange costs).
 
 Timing rules followed: >= 3 warm-up steps; frames rotate through a ring of buffer sets larger than L2
 (so no step finds its input or output in cache from the previous one); the timed region is bracketed by a
@@ -34,6 +36,7 @@ WORKLOADS = {
     "uq-4k-fp16": (2953, 1661, 3840, 2160, "f16", "2953x1661->3840x2160 (true Ultra Quality 1.3x) RGBA16F"),
     "1080p-4k-fp32": (1920, 1080, 3840, 2160, "f32", "1920x1080->3840x2160 EASU+RCAS RGBA32F (BASELINE configs[3])"),
     "2160p-8k-fp16": (3840, 2160, 7680, 4320, "f16", "3840x2160->7680x4320 EASU+RCAS RGBA16F (BASELINE configs[4])"),
+    "1080p-4k-unorm8": (1920, 1080, 3840, 2160, "u8", "1920x1080->3840x2160 EASU+RCAS R8G8B8A8_UNORM (the sample's formats, FSR_Filter.cpp:72-73)"),
 }
 SHARPNESS = 0.25
 RING = 8
@@ -48,6 +51,17 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_issue():
+    """ncu-derived issue-rate data per kernel (tools/ncu_summary.py writes it): inst/px, inst/cycle/SM, pipe utilisation."""
+    p = os.path.join(ROOT, "profiles", "ncu_issue.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
 
 
 def load_traffic():
@@ -135,12 +149,11 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- reference arm
 def cpu_reference_runner():
-    """Returns (kind, fn(frame_f32, ow, oh, y0, y1) -> None) timing the reference's own CPU-compilable source
-    (oracle/_ref) when it was built, else the oracle port."""
+    """Returns (kind, fn) timing the reference's own CPU-compilable source (oracle/_ref) when it was built, else the
+    oracle port."""
     import oracle_lib as ol
     R = ol.ref()
     lib, kind = (R, "reference") if R is not None else (ol.oracle(), "port")
-    import numpy as np
 
     def run(frame, ow, oh, y0, y1, econ, rcon, tmp_holder):
         e0, e1 = max(y0 - 1, 0), min(y1 + 1, oh)
@@ -157,12 +170,38 @@ def cpu_reference_runner():
     return kind, run, ol
 
 
-def time_cpu(wl, steps, warmup, budget_s):
-    """Times the CPU reference on bands of output rows of the workload; returns dict(value, cores, kind, sample, s)."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def omp_runtime():
+    """libgomp of this process (the oracle libraries link it): team size query / override."""
+    try:
+        g = ctypes.CDLL("libgomp.so.1")
+        g.omp_get_max_threads.restype = ctypes.c_int
+        return g
+    except OSError:
+        return None
+
+
+def time_cpu(wl, steps, warmup, budget_s, threads=None):
+    """Times the CPU reference on bands of output rows of the workload with `threads` OpenMP threads (None = all the
+    runtime gives).  Returns dict(value, cores, kind, sample, ...)."""
     import numpy as np
     import fsr1_b200 as F
     iw, ih, ow, oh = wl[:4]
     kind, run, ol = cpu_reference_runner()
+    g = omp_runtime()
+    all_threads = g.omp_get_max_threads() if g else int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    if threads is not None and g:
+        g.omp_set_num_threads(int(threads))
+    team = g.omp_get_max_threads() if g else all_threads
     frame = F.to_half(F.uniform(iw, ih, 12345)).astype(np.float32)
     econ, rcon = ol.easu_con(iw, ih, ow, oh), ol.rcas_con(SHARPNESS)
     holder = (np.zeros((oh, ow, 4), np.float32), np.zeros((oh, ow, 4), np.float32))
@@ -181,10 +220,22 @@ def time_cpu(wl, steps, warmup, budget_s):
         run(frame, ow, oh, y0, y1, econ, rcon, holder)
         px += (y1 - y0) * ow
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
-            "sample": "%d steps x %d-row bands of the %dx%d output, fp32 F path, OpenMP over rows" % (steps, rows, ow, oh),
+    if threads is not None and g:
+        g.omp_set_num_threads(all_threads)
+    return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": team, "kind": kind,
+            "sample": "%d steps x %d-row bands of the %dx%d output, fp32 F path, OpenMP over rows (%d threads)" % (steps, rows, ow, oh, team),
+            "cpu_model": cpu_model(), "logical_cpus": os.cpu_count(), "omp_proc_bind": os.environ.get("OMP_PROC_BIND", "unset"),
             "seconds": dt, "ms_per_step": dt / steps * 1e3}
+
+
+def cpu_baseline(wl):
+    """All host threads (the headline cpu_baseline) and one thread (SURVEY 8(d) asks for both), same run."""
+    allc = time_cpu(wl, steps=12, warmup=1, budget_s=12.0)
+    one = time_cpu(wl, steps=6, warmup=1, budget_s=6.0, threads=1)
+    for d in (allc, one):
+        d.pop("seconds", None)
+    allc["one_thread"] = {"value": one["value"], "unit": "Mpix/s", "cores": 1, "sample": one["sample"]}
+    return allc
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -198,8 +249,9 @@ def run_ours(args, rank, world, local_rank):
     api = F.api
     wl = WORKLOADS[args.workload]
     iw, ih, ow, oh, dts = wl[:5]
-    tdt = torch.float16 if dts == "f16" else torch.float32
-    bpp = 8 if dts == "f16" else 16
+    tdt = {"f16": torch.float16, "f32": torch.float32, "u8": torch.uint8}[dts]
+    bpp = {"f16": 8, "f32": 16, "u8": 4}[dts]
+    fmt = {"f16": api.FORMAT_RGBA16F, "f32": api.FORMAT_RGBA32F, "u8": api.FORMAT_RGBA8_UNORM}[dts]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -208,165 +260,83 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
 
-    def host_frame(seed, rows=None, first=0):
+    def host_frame(seed):
         f = F.uniform(iw, ih, seed)
+        if dts == "u8":
+            return np.floor(f * 255.0 + 0.5).astype(np.uint8)
         return f.astype(np.float16) if dts == "f16" else f
 
-    econ1, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(SHARPNESS)
+    # The frame the job upscales.  N = 1: the workload's frame.  N > 1, default ("weak"): `world` such frames stacked
+    # (1920 x 1080N -> 3840 x 2160N), rank r owning frame r of the stack; --shard-frame ("strong"): the workload's own
+    # frame cut into `world` row slabs (BASELINE configs[4] at N = 8).
+    strong = world > 1 and args.shard_frame
+    H_in, H_out = (ih, oh) if (world == 1 or strong) else (ih * world, oh * world)
+
+    def rank_rows(t, r, o0, o1):
+        """input rows [o0,o1) of the tall frame t owned by rank r"""
+        if world == 1 or strong:
+            return host_frame(12345 + t)[o0:o1]
+        return host_frame(12345 + t + 1000 * r)          # rank r's slab IS frame r of the stack
+
     stream = torch.cuda.current_stream()
-    out = {}
-    pipe = None   # api.FramePipeline when frames are software-pipelined on two streams (default at N=1)
-    if world == 1:
-        def resident(a):  # rows padded to a 16-byte multiple, like any texture allocation (TMA / 128-bit access need it)
-            h, w = a.shape[:2]
-            buf = torch.zeros((h, (w + 1) & ~1, 4), dtype=tdt, device=dev)
-            buf[:, :w] = torch.from_numpy(a).to(dev)
-            return buf[:, :w]
-        ins = [resident(host_frame(12345 + t)) for t in range(RING)]
-        tmps = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
-        outs = [torch.empty((oh, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
-        imgs = [(api.image(ins[i]), api.image(tmps[i]), api.image(outs[i])) for i in range(RING)]
-        prepared = [api.PreparedUpscale(a, t, b, econ1, rcon) for a, t, b in imgs]   # arguments marshalled once per buffer set
-        pipe = None if args.no_pipeline else api.FramePipeline(imgs, econ1, rcon, device=dev)
+    halo_mode = args.halo if world > 1 else "p2p"
+    up = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo=halo_mode,
+                           one_stream=args.no_pipeline)
+    plan = up.plan
+    o0, o1 = plan.owned_in_rows(rank)
+    e0, e1 = plan.easu_rows(rank)
+    y0, y1 = plan.out_rows(rank)
+    for t in range(RING):                                 # every frame's slab is resident in HBM before the clock starts
+        up.input(t).copy_(torch.from_numpy(np.ascontiguousarray(rank_rows(t, rank, o0, o1))).to(dev))
+    torch.cuda.synchronize()
+    halo = plan.halo_bytes(rank, iw, bpp)
+    total_out_px = ow * H_out
 
-        def step_seq(i):
-            prepared[i % RING].launch(stream)
-
+    if halo_mode == "p2p":
         def step(i):
-            if pipe is None:
-                step_seq(i)
-            else:
-                pipe.submit(i % RING)      # RCAS of frame i overlaps EASU of frame i+1 (two streams)
+            up.submit(i % RING, stream)                   # C ABI: halo push + EASU + RCAS, pipelined on the shard's streams
 
-        def step_easu(i):
-            a, t, _ = imgs[i % RING]
-            api.easu(a, t, econ1, stream=stream)
-
-        def step_rcas(i):
-            _, t, b = imgs[i % RING]
-            api.rcas(t, b, rcon, stream=stream)
-        total_out_px = ow * oh
-        halo = 0
+        def drain():
+            for k in range(RING):
+                up.wait(k, stream)
     else:
-        # default ("weak"): the frame is `world` slabs tall, this rank owns input rows [rank*ih, (rank+1)*ih) of it;
-        # --shard-frame ("strong"): the named frame itself is cut into `world` row slabs (BASELINE configs[4] at N=8)
-        H_in, H_out = (ih, oh) if args.shard_frame else (ih * world, oh * world)
-        ups = [F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev) for _ in range(RING)]
-        for t, u in enumerate(ups):  # each frame's slab is resident in HBM inside its halo window
-            src = torch.from_numpy(host_frame(12345 + t + (0 if args.shard_frame else 1000 * rank))).to(dev)
-            o0, o1 = u.plan.owned_in_rows(rank)
-            u.owned.copy_(src[o0:o1] if args.shard_frame else src)
-        if args.graph:
-            for u in ups:            # halo exchange + EASU + RCAS recorded once; a step is one graph launch
-                u.capture()
+        # NCCL data plane (torch.distributed send/recv): the halo rows of frame i+1 travel on a second stream while
+        # frame i is upscaled; kernels of frame i+1 wait on that exchange's event only
+        comm = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(RING)]
 
-            def step(i):
-                ups[i % RING].upscale()
-        elif args.no_overlap:
-            def step(i):
-                ups[i % RING].upscale()
-        elif args.halo_depth > 1 or args.pipeline_sharded or args.halo_batch > 1:
-            # EXPERIMENTAL (not the default): halo exchange `halo_depth` frames ahead (more slack against rank-to-rank
-            # jitter than the one-frame prefetch below) and, with --pipeline-sharded, RCAS of frame i on a second
-            # stream while EASU of frame i+1 runs (api.FramePipeline over the slab windows), as at N=1
-            depth = max(1, min(args.halo_depth, RING - 1))
-            comm = torch.cuda.Stream(device=dev)
-            ready = [torch.cuda.Event() for _ in range(RING)]
-            done = [torch.cuda.Event() for _ in range(RING)]
-            used = [False] * RING
-            if args.pipeline_sharded:
-                u0 = ups[0]
-                e0, e1 = u0.plan.easu_rows(rank)
-                y0, y1 = u0.plan.out_rows(rank)
-                pipe = api.FramePipeline(
-                    [(api.image(u.window, height=u.in_h, row0=u._win0), api.image(u.tmp, height=u.out_h, row0=e0),
-                      api.image(u.out, height=u.out_h, row0=y0)) for u in ups],
-                    ups[0].econ, ups[0].rcon, device=dev, easu_rows=(e0, e1), rcas_rows=(y0, y1))
+        def prefetch(j):
+            comm.wait_stream(stream)
+            with torch.cuda.stream(comm):
+                up._exchange(j % RING)
+                ready[j % RING].record(comm)
+        prefetch(0)
+        frame_no = [0]
 
-            def prefetch(j):
-                k = j % RING
-                if used[k]:
-                    comm.wait_event(done[k])     # frame j-RING, the window's previous reader
-                with torch.cuda.stream(comm):
-                    ups[k]._exchange()
-                    ready[k].record(comm)
-            batch = max(1, min(args.halo_batch, RING // 2))
+        def step(_):
+            i = frame_no[0]
+            frame_no[0] += 1
+            prefetch(i + 1)
+            stream.wait_event(ready[i % RING])
+            up._launch(i % RING, stream)
 
-            def prefetch_group(g):               # --halo-batch: the halos of `batch` consecutive frames in ONE NCCL group
-                slots = [(g * batch + t) % RING for t in range(batch)]
-                for k in slots:
-                    if used[k]:
-                        comm.wait_event(done[k])
-                with torch.cuda.stream(comm):
-                    F.ShardedUpscaler.exchange_many([ups[k] for k in slots])
-                    for k in slots:
-                        ready[k].record(comm)
-            if batch > 1:
-                prefetch_group(0)
-            else:
-                for j in range(depth):
-                    prefetch(j)
-            frame = [0]
+        def drain():
+            stream.wait_stream(comm)
 
-            def step(_):
-                i = frame[0]
-                frame[0] += 1
-                k = i % RING
-                if batch > 1:
-                    if i % batch == 0:
-                        prefetch_group(i // batch + 1)
-                else:
-                    prefetch(i + depth)
-                if pipe is not None:
-                    pipe.stream_easu.wait_event(ready[k])
-                    pipe.submit(k)
-                    done[k].record(pipe.stream_easu)      # EASU is the only reader of the window
-                else:
-                    stream.wait_event(ready[k])
-                    ups[k]._launch(stream)
-                    done[k].record(stream)
-                used[k] = True
-        else:
-            # frame pipeline: while frame i is upscaled, the halo rows of frame i+1 (already resident) travel on a
-            # second stream; kernels of frame i+1 wait on that exchange's event only
-            comm = torch.cuda.Stream(device=dev)
-            ready = [torch.cuda.Event() for _ in range(RING)]
-
-            def prefetch(j):
-                u = ups[j % RING]
-                comm.wait_stream(stream)         # the window's previous readers (frame j-RING) are ordered before
-                with torch.cuda.stream(comm):
-                    u._exchange()
-                    ready[j % RING].record(comm)
-            prefetch(0)
-            frame = [0]
-
-            def step(_):
-                i = frame[0]
-                frame[0] += 1
-                prefetch(i + 1)
-                stream.wait_event(ready[i % RING])
-                ups[i % RING]._launch(stream)
-        step_easu = step_rcas = None
-        total_out_px = ow * H_out
-        halo = ups[0].plan.halo_bytes(rank, iw, bpp)
-
-    def timed(fn, n, pre=None, post=None):
+    def timed(fn, n, post=None):
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        if pre:
-            pre()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
         for i in range(n):
             fn(i)
         if post:
             post()
-        e1.record(stream)
+        b.record(stream)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = a.elapsed_time(b)
         if dist is not None:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -376,116 +346,230 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(W):
         step(i)
+    drain()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = api.launch_count()
-    piped = pipe is not None
-    ms = timed(step, K, pre=(lambda: pipe.begin(stream)) if piped else None, post=(lambda: pipe.end(stream)) if piped else None)
+    ms = timed(step, K, post=drain)
     launches = api.launch_count() - launches0
-    if world > 1 and args.graph:
-        launches = 2 * K  # each replayed graph holds this library's two kernels (EASU, RCAS), recorded at capture
     clocks = sampler.stop() if rank == 0 else None
+    up.status()
     value = total_out_px * K / (ms * 1e-3) / 1e6
-
     peak, peak_src = load_peaks()
-    kernels, roofline = {}, None
-    latency_ms = None
-    if world == 1:
-        if piped:
-            for i in range(W):
-                step_seq(i)
-            latency_ms = timed(step_seq, K) / K      # one frame at a time on one stream: EASU then RCAS, no overlap
-        Pin, Pout = iw * ih, ow * oh
-        alg = {"easu": bpp * (Pin + Pout), "rcas": bpp * 2 * Pout}
-        names = {}
-        for key, fn in (("easu", step_easu), ("rcas", step_rcas)):
-            for i in range(W):
-                fn(i)
-            names[key] = api.last_kernel()
-            kms = timed(fn, K) / K
-            gbs = alg[key] / (kms * 1e-3) / 1e9
-            kernels[key] = {"kernel": names[key], "us": kms * 1e3, "algorithmic_bytes": alg[key], "GBps": gbs,
-                            "frac_of_hbm_peak": gbs / peak}
-        dom = max(kernels, key=lambda k: kernels[k]["us"])
-        traffic = load_traffic().get(kernels[dom]["kernel"])
-        roofline = {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["GBps"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg[dom], "us_per_launch": kernels[dom]["us"],
-                    "note": "EASU is instruction-issue-bound on B200, not HBM-bound: 182 instructions per output pixel at the "
-                            "2.1-2.6 inst/cycle/SM this mix can issue (HFMA2, FFMA2 and scalar FFMA all sustain ~2 inst/cycle/SM: "
-                            "profiles/r01_ubench_pipes.txt) is >= 58 us per 4K frame vs 12.6 us at the HBM roofline; the kernel "
-                            "runs at 2.53 inst/cycle/SM (ncu: profiles/r01_ncu_summary.txt, DESIGN.md section 4)"}
-        path_bytes = alg["easu"] + alg["rcas"]
-        kernels["path"] = {"algorithmic_bytes": path_bytes, "us": ms / K * 1e3,
-                           "GBps": path_bytes / (ms / K * 1e-3) / 1e9, "frac_of_hbm_peak": path_bytes / (ms / K * 1e-3) / 1e9 / peak}
 
-    # ---- end to end: host (pinned) -> device -> kernels -> host, through the C ABI's host-frame entry point
+    # ---- the same frames one at a time on one stream (no overlap of consecutive frames): latency view
+    latency_ms = None
+    if world == 1 and not args.no_pipeline:
+        seq = F.ShardedUpscaler(iw, ih, ow, oh, 1, 0, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo="p2p", one_stream=True)
+        for t in range(RING):
+            seq.input(t).copy_(up.input(t))
+
+        def seq_step(i):
+            seq.submit(i % RING, stream)
+        for i in range(W):
+            seq_step(i)
+        latency_ms = timed(seq_step, K, post=lambda: [seq.wait(k, stream) for k in range(RING)]) / K
+        seq.close()
+
+    # ---- per-kernel times on this rank's slab (max over ranks) and the roofline of the dominant kernel
+    tmps = [torch.empty((e1 - e0, ow, 4), dtype=tdt, device=dev) for _ in range(RING)]
+    win_imgs = [api.image(up.windows[t], height=H_in, row0=up._win0) for t in range(RING)]
+    tmp_imgs = [api.image(tmps[t], height=H_out, row0=e0) for t in range(RING)]
+    out_imgs = [api.image(up.outputs[t], height=H_out, row0=y0) for t in range(RING)]
+
+    def step_easu(i):
+        api.easu(win_imgs[i % RING], tmp_imgs[i % RING], up.econ, y0=e0, y1=e1, stream=stream)
+
+    def step_rcas(i):
+        api.rcas(tmp_imgs[i % RING], out_imgs[i % RING], up.rcon, y0=y0, y1=y1, stream=stream)
+    Pin, Pout = iw * (o1 - o0), ow * (y1 - y0)
+    alg = {"easu": bpp * (Pin + Pout), "rcas": bpp * 2 * Pout}
+    kernels = {}
+    for key, fn in (("easu", step_easu), ("rcas", step_rcas)):
+        for i in range(W):
+            fn(i)
+        name = api.last_kernel()
+        kms = timed(fn, K) / K
+        gbs = alg[key] / (kms * 1e-3) / 1e9
+        kernels[key] = {"kernel": name, "us": kms * 1e3, "algorithmic_bytes": alg[key], "GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    del tmps
+    dom = max(kernels, key=lambda k: kernels[k]["us"])
+    traffic = load_traffic().get(kernels[dom]["kernel"])
+    issue = load_issue().get(kernels[dom]["kernel"])
+    roofline = {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["GBps"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "us_per_launch": kernels[dom]["us"], "per": "GPU (max over ranks)",
+                "issue": issue}
+    path_bytes = alg["easu"] + alg["rcas"]
+    per_frame_us = ms / K * 1e3
+    kernels["path"] = {"algorithmic_bytes": path_bytes, "us": per_frame_us, "GBps": path_bytes / (per_frame_us * 1e-6) / 1e9,
+                       "frac_of_hbm_peak": path_bytes / (per_frame_us * 1e-6) / 1e9 / peak}
+
+    # ---- N > 1: parity of the sharded result, and what the halo exchange costs
+    parity, halo_info = None, None
+    if world > 1:
+        parity = check_sharded_parity(F, api, up, dist, dev, rank, world, iw, ih, ow, oh, H_in, H_out, tdt, rank_rows, halo_mode)
+        nh = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo="p2p",
+                               one_stream=args.no_pipeline, skip_halo=True)
+        for t in range(RING):
+            nh.input(t).copy_(up.input(t))
+
+        def nh_step(i):
+            nh.submit(i % RING, stream)
+        for i in range(W):
+            nh_step(i)
+        ms_nh = timed(nh_step, K, post=lambda: [nh.wait(k, stream) for k in range(RING)])
+        nh.close()
+        halo_info = {"mode": halo_mode, "recv_bytes_per_step_per_rank": halo, "us_per_step_without_exchange": ms_nh / K * 1e3,
+                     "exposed_us_per_step": (ms - ms_nh) / K * 1e3,
+                     "how": "same schedule re-timed with FSR1_SHARD_SKIP_HALO (no push / wait / credit kernels)"}
+
+    # ---- end to end: host (pinned) -> device -> kernels -> host
     e2e = None
+    Ke = max(3, min(K, 60))
     if world == 1:
         NS = 3
-        ctxs = [api.HostContext(iw, ih, ow, oh, api.FORMAT_RGBA16F if dts == "f16" else api.FORMAT_RGBA32F) for _ in range(NS)]
+        ctxs = [api.HostContext(iw, ih, ow, oh, fmt) for _ in range(NS)]
         streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
         hin = [torch.from_numpy(host_frame(777 + t)).pin_memory() for t in range(NS)]
-        hout = [torch.empty((oh, ow, 4), dtype=tdt).pin_memory() for _ in range(NS)]
-        Ke = max(3, min(K, 60))
+        hout = [torch.empty((oh, ow, 4), dtype=tdt).pin_memory() for t in range(NS)]
 
         def e2e_step(i):
             j = i % NS
             ctxs[j].upscale_host(hin[j], hout[j], SHARPNESS, stream=streams[j])
-        for i in range(NS * 2):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": ow * oh * Ke / dt / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": iw * ih * bpp,
-               "d2h_bytes_per_step": ow * oh * bpp, "steps": Ke, "ms_per_step": dt / Ke * 1e3,
-               "how": "fsr1_context_upscale_host on pinned host frames, %d streams round-robin" % NS}
-        checks = float(hout[0][::97, ::89, :3].float().sum())  # the result is really read on the host
-        e2e["host_checksum"] = checks
+        how = "fsr1_context_upscale_host on pinned host frames, %d streams round-robin" % NS
+    else:
+        NS = min(3, RING)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+        hin = [torch.from_numpy(np.ascontiguousarray(rank_rows(50 + t, rank, o0, o1))).pin_memory() for t in range(NS)]
+        hout = [torch.empty((y1 - y0, ow, 4), dtype=tdt).pin_memory() for t in range(NS)]
+        for st in streams:
+            st.wait_stream(stream)
+
+        def e2e_step(i):
+            j = i % NS
+            with torch.cuda.stream(streams[j]):
+                up.input(j).copy_(hin[j], non_blocking=True)
+                up.submit(j, streams[j])
+                up.wait(j, streams[j])
+                hout[j].copy_(up.output(j), non_blocking=True)
+        how = "every rank: pinned host slab -> fsr1_shard input, fsr1_shard_submit/wait, output slab -> pinned host; %d slots round-robin" % NS
+    for i in range(NS * 2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": total_out_px * Ke / dt / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": iw * H_in * bpp,
+           "d2h_bytes_per_step": ow * H_out * bpp, "steps": Ke, "ms_per_step": dt / Ke * 1e3, "how": how,
+           "host_checksum": float(hout[0][::97, ::89, :3].float().sum())}   # the result is really read on the host
+    if world == 1:
         for c in ctxs:
             c.close()
+    up.status()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = time_cpu(wl, steps=12, warmup=1, budget_s=15.0)
-        cpu.pop("seconds", None)
+        cpu = cpu_baseline(wl)
 
     if rank == 0:
+        shard_desc = "" if world == 1 else (" cut into %d row slabs" % world if strong else " x%d slabs tall, row-slab sharded" % world)
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (world > 1 and args.shard_frame) else "weak", "vs_baseline": None,
-            "dtype": "f16" if dts == "f16" else "f32", "data": "synthetic",
-            "config": {"workload": wl[5] if world == 1 else wl[5] + (" cut into %d row slabs, NCCL halo" % world if args.shard_frame else " x%d slabs tall, row-slab sharded, NCCL halo" % world),
-                       "sharpness_stops": SHARPNESS, "frame": "LCG uniform noise, seed 12345+t",
-                       "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * ih + 2 * ow * oh) * bpp / 1e6),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": dts, "data": "synthetic",
+            "config": {"workload": wl[5] + shard_desc, "sharpness_stops": SHARPNESS, "frame": "LCG uniform noise, seed 12345+t",
+                       "l2": "ring of %d frame sets (%.0f MB per rank) > 126 MB L2" % (RING, RING * (iw * (o1 - o0) + 2 * ow * (y1 - y0)) * bpp / 1e6),
                        "parallelism": "1 GPU" if world == 1 else "row-slab x%d, %d B halo recv per rank per step, %s" % (
-                           world, halo, "one CUDA graph per frame" if args.graph else ("halo exchange in line" if args.no_overlap else (
-                               "EXPERIMENTAL: halo exchange %s%s" % ("of %d frames per NCCL group" % args.halo_batch if args.halo_batch > 1 else "%d frames ahead" % args.halo_depth,
-                                                                      ", RCAS/EASU of consecutive frames on two streams" if args.pipeline_sharded else "")
-                               if (args.halo_depth > 1 or args.pipeline_sharded or args.halo_batch > 1) else "halo exchange of frame i+1 overlapped with frame i on a second stream")))},
-            "gpu_launches": int(launches), "clocks": clocks,
+                           world, halo, "direct NVLink stores into the neighbour's window (CUDA IPC, fsr1_shard_*), no NCCL in the step"
+                           if halo_mode == "p2p" else "NCCL send/recv one frame ahead on a second stream"),
+                       "pipelining": "none: EASU then RCAS of each frame on one stream" if args.no_pipeline else
+                                     "RCAS of frame i overlaps EASU of frame i+1 (two streams inside fsr1_shard), same schedule at every N"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "e2e": e2e,
         }
-        if world == 1:
-            line["config"]["pipelining"] = ("two CUDA streams: RCAS of frame i overlaps EASU of frame i+1 (api.FramePipeline)"
-                                            if piped else "none: EASU then RCAS of each frame on one stream")
-            if latency_ms is not None:
-                line["unpipelined_ms_per_step"] = latency_ms
-                line["unpipelined_value"] = total_out_px / (latency_ms * 1e-3) / 1e6
-        if roofline:
-            line["roofline"] = roofline
-            line["kernels"] = kernels
+        if latency_ms is not None:
+            line["unpipelined_ms_per_step"] = latency_ms
+            line["unpipelined_value"] = total_out_px / (latency_ms * 1e-3) / 1e6
+        if parity is not None:
+            line["parity"] = parity
+        if halo_info is not None:
+            line["halo"] = halo_info
         if cpu:
             line["cpu_baseline"] = cpu
-        if e2e:
-            line["e2e"] = e2e
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+    up.close()
+    if dist is not None:
         dist.destroy_process_group()
+
+
+def check_sharded_parity(F, api, up, dist, dev, rank, world, iw, ih, ow, oh, H_in, H_out, tdt, rank_rows, halo_mode):
+    """Outside the timed region: frame 0 once more through the sharded path, every rank's slab sent to rank 0, which upscales the
+    whole frame on its own GPU and compares bit for bit; then against the oracle on bands that straddle slab boundaries; then
+    the OTHER halo data plane against this one."""
+    import numpy as np
+    import torch
+    import oracle_lib as ol
+    stream = torch.cuda.current_stream()
+    plan = up.plan
+    o0, o1 = plan.owned_in_rows(rank)
+    up.input(0).copy_(torch.from_numpy(np.ascontiguousarray(rank_rows(0, rank, o0, o1))).to(dev))
+    up.submit(0, stream)
+    up.wait(0, stream)
+    torch.cuda.synchronize()
+    mine = up.output(0).contiguous().clone()
+    # the other data plane, one frame, same input
+    other_mode = "nccl" if halo_mode == "p2p" else "p2p"
+    other = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=1, halo=other_mode)
+    other.input(0).copy_(up.input(0))
+    other.submit(0, stream)
+    other.wait(0, stream)
+    torch.cuda.synchronize()
+    same = torch.tensor([1 if torch.equal(other.output(0), mine) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    other.close()
+    result = {"%s_equals_%s" % (other_mode, halo_mode): bool(same.item())}
+    if rank != 0:
+        dist.send(mine, 0)
+        return None
+    slabs = [mine]
+    for r in range(1, world):
+        a, b = plan.out_rows(r)
+        t = torch.empty((b - a, ow, 4), dtype=tdt, device=dev)
+        dist.recv(t, r)
+        slabs.append(t)
+    full = np.concatenate([rank_rows(0, r, *plan.owned_in_rows(r)) for r in range(world)])
+    full_t = torch.from_numpy(np.ascontiguousarray(full)).to(dev)
+    tmp = torch.empty((H_out, ow, 4), dtype=tdt, device=dev)
+    whole = torch.empty((H_out, ow, 4), dtype=tdt, device=dev)
+    api.upscale(full_t, tmp, whole, up.econ, up.rcon)
+    torch.cuda.synchronize()
+    eq = all(torch.equal(slabs[r], whole[plan.out_rows(r)[0]:plan.out_rows(r)[1]]) for r in range(world))
+    result["sharded_equals_single_gpu"] = bool(eq)
+    # oracle on bands: the top of the frame and 32 rows around the first and last slab boundaries
+    f32 = full.astype(np.float32) if full.dtype != np.uint8 else full.astype(np.float32) / 255.0
+    got = torch.cat(slabs).cpu().numpy()
+    got = got.astype(np.float32) if got.dtype != np.uint8 else got.astype(np.float32) / 255.0
+    worst = 0.0
+    bands = [(0, 32)] + [(plan.out_rows(r)[0] - 16, plan.out_rows(r)[0] + 16) for r in sorted({1, world - 1})]
+    for (a, b) in bands:
+        e = ol.easu(f32, ow, H_out, y0=max(a - 1, 0), y1=min(b + 1, H_out))
+        want = ol.rcas(e, ol.rcas_con(SHARPNESS), y0=a, y1=b)
+        worst = max(worst, float(np.abs(got[a:b] - want[a:b])[..., :3].max()))
+    result["max_abs_vs_oracle"] = worst
+    result["oracle_bands"] = bands
+    result["tolerance"] = 1e-2 if tdt != torch.float32 else 1e-5
+    return result
 
 
 def run_reference(args, rank):
@@ -503,7 +587,8 @@ def run_reference(args, rank):
             "config": {"workload": wl[5], "sharpness_stops": SHARPNESS,
                        "note": "the reference ships no CPU pixel path; this is its own FsrEasuF/FsrRcasF source compiled "
                                "for the host (oracle/_ref) or, if that was not built, the oracle port"},
-            "cpu_baseline": {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                             "cpu_model": r["cpu_model"], "logical_cpus": r["logical_cpus"]},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -517,18 +602,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-4k-fp16", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-pipeline", action="store_true", help="N=1: run EASU and RCAS of each frame back to back on one stream (no frame overlap)")
+    ap.add_argument("--no-pipeline", action="store_true", help="EASU and RCAS of each frame back to back on one stream (no frame overlap)")
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
-    ap.add_argument("--halo-depth", type=int, default=1, help="multi-GPU (experimental): exchange halos this many frames ahead (default 1 = the measured configuration)")
-    ap.add_argument("--halo-batch", type=int, default=1, help="multi-GPU (experimental): exchange the halos of this many consecutive frames in one NCCL group (<= ring/2)")
-    ap.add_argument("--pipeline-sharded", action="store_true", help="multi-GPU (experimental): overlap RCAS of frame i with EASU of frame i+1 on two streams, as at N=1")
-    ap.add_argument("--graph", action="store_true", help="multi-GPU (experimental): replay one CUDA graph per frame (NCCL send/recv + kernels)")
-    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos in line with the kernels instead of one frame ahead")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo data plane: direct NVLink stores through the C ABI (default) or NCCL send/recv")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the reference's OpenMP team: one thread per logical CPU, threads pinned (must be set before libgomp loads)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
     if args.impl == "reference":
         return run_reference(args, rank)
     if args.gpus > 1 and world == 1:

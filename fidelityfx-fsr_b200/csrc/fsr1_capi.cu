@@ -119,6 +119,7 @@ const char* fsr1_error_string(int err) {
     case FSR1_ERR_WINDOW: return "image window does not hold the rows this pass touches";
     case FSR1_ERR_CUDA: return "CUDA error (see fsr1_last_cuda_error)";
     case FSR1_ERR_NO_DEVICE: return "no usable CUDA device";
+    case FSR1_ERR_TIMEOUT: return "a neighbouring rank's halo rows or credit did not arrive in time";
     default: return "unknown fsr1 error";
   }
 }
@@ -179,8 +180,8 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_easu_f32_tiled(p, s, &name);
   } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
-             !(flags & FSR1_FLAG_FORCE_DIRECT)) {
-    e = launch_easu_u_tiled(p, (int)in->format, s, &name);
+             !(flags & (FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_PRECISE))) {
+    e = launch_easu_u_tiled(p, (int)in->format, s, &name);  // half2 taps; FSR1_FLAG_PRECISE keeps the fp32 direct kernel
   }
   if (e == cudaErrorNotSupported) e = launch_easu_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);
@@ -202,6 +203,11 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   if (!window_holds(out, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
   const int need0 = y0 == 0 ? 0 : (int)y0 - 1, need1 = y1 >= out->height ? (int)out->height - 1 : (int)y1;
   if (!window_holds(in, need0, need1)) return FSR1_ERR_WINDOW;
+  {  // RCAS reads neighbours of every pixel it writes: in place is a race
+    const uintptr_t a0 = (uintptr_t)in->data, a1 = a0 + (uintptr_t)in->pitch_bytes * in->rows;
+    const uintptr_t b0 = (uintptr_t)out->data, b1 = b0 + (uintptr_t)out->pitch_bytes * out->rows;
+    if (a0 < b1 && b0 < a1) return FSR1_ERR_INVALID_ARGUMENT;
+  }
 
   RcasParams p;
   p.in = view_of(in);
@@ -226,7 +232,7 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_rcas_f32_packed(p, s, &name);
   } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
-             !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+             !(flags & (FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_PRECISE))) {
     e = launch_rcas_u_packed(p, (int)in->format, s, &name);
   }
   if (e == cudaErrorNotSupported) e = launch_rcas_direct(p, (int)in->format, exact, s, &name);
@@ -304,15 +310,23 @@ void fsr1_context_destroy(fsr1_context* c) {
 }
 
 static int context_run(fsr1_context* c, void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
-                       float sharpness, uint32_t flags, void* stream) {
-  fsr1_image in = {in_dev, in_pitch, c->in_w, c->in_h, 0, c->in_h, c->format, 0};
+                       float sharpness, uint32_t flags, void* stream, uint32_t render_w = 0, uint32_t render_h = 0) {
+  if (render_w == 0) render_w = c->in_w;
+  if (render_h == 0) render_h = c->in_h;
+  fsr1_image in = {in_dev, in_pitch, render_w, render_h, 0, render_h, c->format, 0};
   fsr1_image tmp = {c->tmp, c->tmp_pitch, c->out_w, c->out_h, 0, c->out_h, c->format, 0};
   fsr1_image out = {out_dev, out_pitch, c->out_w, c->out_h, 0, c->out_h, c->format, 0};
   uint32_t econ[16], rcon[4];
   // exactly what FSR_Filter::Upscale passes (sample/src/DX12/FSR_Filter.cpp:106,124)
-  fsr1_easu_con(econ, (float)c->in_w, (float)c->in_h, (float)c->in_w, (float)c->in_h, (float)c->out_w, (float)c->out_h);
+  fsr1_easu_con(econ, (float)render_w, (float)render_h, (float)render_w, (float)render_h, (float)c->out_w, (float)c->out_h);
   fsr1_rcas_con(rcon, sharpness);
   return fsr1_upscale(&in, &tmp, &out, econ, rcon, 0, c->out_h, flags, stream);
+}
+
+int fsr1_context_upscale_render(fsr1_context* c, const void* in_dev, uint64_t in_pitch, uint32_t render_w, uint32_t render_h,
+                                void* out_dev, uint64_t out_pitch, float sharpness, uint32_t flags, void* stream) {
+  if (!c || !in_dev || !out_dev || !render_w || !render_h) return FSR1_ERR_INVALID_ARGUMENT;
+  return context_run(c, const_cast<void*>(in_dev), in_pitch, out_dev, out_pitch, sharpness, flags, stream, render_w, render_h);
 }
 
 int fsr1_context_upscale(fsr1_context* c, const void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
@@ -327,11 +341,14 @@ int fsr1_context_upscale_host(fsr1_context* c, const void* in_host, uint64_t in_
   const uint64_t bpp = (uint64_t)bytes_per_pixel(c->format);
   if (in_pitch < c->in_w * bpp || out_pitch < c->out_w * bpp) return FSR1_ERR_INVALID_ARGUMENT;
   cudaError_t e;
-  if (!c->dev_in) {
+  if (!c->dev_in || !c->dev_out) {  // both or neither: a failed second allocation leaves nothing half-initialised
     c->in_pitch = ((uint64_t)c->in_w * bpp + 127) & ~(uint64_t)127;
     c->out_pitch = ((uint64_t)c->out_w * bpp + 127) & ~(uint64_t)127;
-    if ((e = cudaMalloc(&c->dev_in, c->in_pitch * c->in_h)) != cudaSuccess) return cuda_fail(e);
-    if ((e = cudaMalloc(&c->dev_out, c->out_pitch * c->out_h)) != cudaSuccess) return cuda_fail(e);
+    void *din = nullptr, *dout = nullptr;
+    if ((e = cudaMalloc(&din, c->in_pitch * c->in_h)) != cudaSuccess) return cuda_fail(e);
+    if ((e = cudaMalloc(&dout, c->out_pitch * c->out_h)) != cudaSuccess) { cudaFree(din); return cuda_fail(e); }
+    c->dev_in = din;
+    c->dev_out = dout;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   e = cudaMemcpy2DAsync(c->dev_in, c->in_pitch, in_host, in_pitch, c->in_w * bpp, c->in_h, cudaMemcpyHostToDevice, s);

@@ -16,6 +16,13 @@ struct ImgView {
   int row0, rows;   // stored window
 };
 
+// Logical row y is inside the image AND inside the stored window.  The checked load paths of the RCAS kernels test
+// this (not just 0 <= y < h): a lane requests kRows+2 rows up front, and the last partial chunk of a row slab would
+// otherwise read up to kRows-1 rows past the rows the window is required to hold.
+__host__ __device__ __forceinline__ bool row_stored(const ImgView& im, int y) {
+  return y >= im.row0 && y < im.row0 + im.rows && y >= 0 && y < im.h;
+}
+
 struct EasuParams {
   ImgView in, out;
   float c0x, c0y, c0z, c0w;  // con0 of FsrEasuCon: scale.xy, offset.zw
@@ -144,14 +151,6 @@ template <> struct Px<Unorm10> {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// Development knobs: integer environment variables read once per process (thread-safe through a function-local static
-// at each use site).  They select measured-and-rejected or not-yet-measured kernel variants; the defaults are the
-// production configuration and nothing in the public API depends on them.
-static inline int env_knob(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 // launchers (defined in the .cu files, called from fsr1_capi.cu)
 cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cudaStream_t s, const char** name);
@@ -159,7 +158,7 @@ cudaError_t launch_rcas_direct(const RcasParams& p, int format, bool exact, cuda
 // meet their alignment needs (the caller then falls back to the direct kernels).
 cudaError_t launch_easu_h_tiled(const EasuParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char** name);
-// UNORM images through TMA-tiled kernels (experimental, FSR1_UNORM_TILED=1): cudaErrorNotSupported unless enabled and applicable
+// UNORM images through the TMA-tiled 2x EASU / packed RCAS kernels: cudaErrorNotSupported when not applicable
 cudaError_t launch_easu_u_tiled(const EasuParams& p, int format, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_u_packed(const RcasParams& p, int format, cudaStream_t s, const char** name);
 cudaError_t launch_easu_f32_tiled(const EasuParams& p, cudaStream_t s, const char** name);  // RGBA32F, exactly 2x

@@ -65,30 +65,6 @@ __device__ __forceinline__ float4 texel_terms(float lA, float lB, float lC, floa
   return make_float4(dirX, dirY, fmaf(lenX, lenX, lenY * lenY), 0.0f);
 }
 
-// Per-pixel filter shape from the blended (dir, len): the coefficients the tap loop needs.  fp32.
-struct Shape { float qa, qb, qc, lob, clp; };
-__device__ __forceinline__ Shape pixel_shape(float dx, float dy, float len) {
-  const float dirR = fmaf(dx, dx, dy * dy);
-  const bool zro = dirR < (1.0f / 32768.0f);
-  const float rs = zro ? 1.0f : prx_lo_rsq(dirR);
-  dx = (zro ? 1.0f : dx) * rs;
-  dy *= rs;
-  len *= 0.5f;
-  len *= len;
-  const float dx2 = dx * dx, dy2 = dy * dy;
-  const float stretch = (dx2 + dy2) * prx_lo_rcp(fmaxf(fabsf(dx), fabsf(dy)));
-  const float l2x = fmaf(stretch - 1.0f, len, 1.0f), l2y = fmaf(-0.5f, len, 1.0f);
-  Shape s;
-  s.lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
-  s.clp = prx_lo_rcp(s.lob);
-  const float X2 = l2x * l2x, Y2 = l2y * l2y;
-  s.qa = fmaf(X2, dx2, Y2 * dy2);
-  s.qc = fmaf(X2, dy2, Y2 * dx2);
-  s.qb = (dx * dy * 2.0f) * (X2 - Y2);
-  return s;
-}
-
-
 #ifndef FSR1_CPU_EMU
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

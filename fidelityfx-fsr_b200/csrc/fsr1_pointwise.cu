@@ -156,26 +156,15 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const PointPar
   }
 }
 
-// development knobs: FSR1_POINT_LAYOUT = 0 (256 x N CTAs), 1 = default (256N x 1 CTAs: 8 % faster on RGBA16F, one
-// contiguous stretch of a row per CTA); FSR1_POINT_N = 4 (default) | 8 pixels per thread (slower: registers)
-template <typename SI, typename SO, int N>
-static cudaError_t launch_n(const PointParams& p, cudaStream_t s, int layout) {
-  const int aux_step = p.aux_format ? kPointThreads % p.aux.w : 0;
-  if (layout == 1) {
-    const int per_cta = kPointThreads * N;
-    const dim3 grid((p.out.w + per_cta - 1) / per_cta, p.y1 - p.y0, 1);
-    pointwise_kernel<SI, SO, true, N><<<grid, kPointThreads, 0, s>>>(p, aux_step);
-  } else {
-    const dim3 grid((p.out.w + kPointThreads - 1) / kPointThreads, (p.y1 - p.y0 + N - 1) / N, 1);
-    pointwise_kernel<SI, SO, false, N><<<grid, kPointThreads, 0, s>>>(p, aux_step);
-  }
-  return cudaGetLastError();
-}
-
 template <typename SI, typename SO>
 static cudaError_t launch_one(const PointParams& p, cudaStream_t s) {
-  static const int layout = env_knob("FSR1_POINT_LAYOUT", 1), n = env_knob("FSR1_POINT_N", kRowsPerThread);
-  return n == 8 ? launch_n<SI, SO, 8>(p, s, layout) : launch_n<SI, SO, kRowsPerThread>(p, s, layout);
+  // a CTA covers a contiguous stretch of one row (measured: +8 % over a 256x4-pixel CTA on RGBA16F; 8 pixels per thread
+  // is slower: registers)
+  const int aux_step = p.aux_format ? kPointThreads % p.aux.w : 0;
+  const int per_cta = kPointThreads * kRowsPerThread;
+  const dim3 grid((p.out.w + per_cta - 1) / per_cta, p.y1 - p.y0, 1);
+  pointwise_kernel<SI, SO, true, kRowsPerThread><<<grid, kPointThreads, 0, s>>>(p, aux_step);
+  return cudaGetLastError();
 }
 
 // in_format == out_format for every op; TEPD may also write its 8/10-bit code values straight into a UNORM image

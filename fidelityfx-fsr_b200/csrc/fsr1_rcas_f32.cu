@@ -18,6 +18,7 @@ __device__ __forceinline__ PxF load_one(const RcasParams& p, int x, int y) {
   if (kChecked) {
     if (p.clamp) { x = clampi(x, 0, p.in.w - 1); y = clampi(y, 0, p.in.h - 1); }
     else if (x < 0 || y < 0 || x >= p.in.w || y >= p.in.h) return PxF{0.f, 0.f, 0.f};
+    if (!row_stored(p.in, y)) return PxF{0.f, 0.f, 0.f};  // prefetched past the row range of a window: never used
   }
   const float4 v = __ldg(reinterpret_cast<const float4*>(p.in.base + (long long)(y - p.in.row0) * p.in.pitch) + x);
   return PxF{v.x, v.y, v.z};
@@ -26,35 +27,30 @@ template <bool kChecked> __device__ __forceinline__ PairF load_two(const RcasPar
   return PairF{load_one<kChecked>(p, x, y), load_one<kChecked>(p, x + 1, y)};
 }
 
-// kApprox (experimental, FSR1_RCAS_F32_VARIANT=1): MUFU.RCP (rcp.approx.f32, 1 ulp, denormals handled) instead of the
-// IEEE-rounded __frcp_rn, whose refinement and slow-path call are a quarter of this kernel's instructions; the fast
-// fp32 path is held to 1e-5 of the oracle, not to bit-exactness (that is FSR1_FLAG_EXACT).
-template <bool kApprox> __device__ __forceinline__ float rcp_f(float a) {
-  if constexpr (kApprox) {
+// Reciprocals: MUFU.RCP (rcp.approx.f32, 1 ulp, denormals handled) instead of the IEEE-rounded __frcp_rn, whose
+// refinement and slow-path call were a quarter of this kernel's instructions (measured on B200: 65.1 -> 52.6 us per 4K
+// frame, profiles/r02_variants.log); the fast fp32 path is held to 1e-5 of the oracle, not to bit-exactness (that is
+// FSR1_FLAG_EXACT).
+__device__ __forceinline__ float rcp_f(float a) {
 #ifdef FSR1_CPU_EMU
-    return 1.0f / a;
+  return 1.0f / a;
 #else
-    float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
-    return r;
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 #endif
-  } else {
-    return __frcp_rn(a);
-  }
 }
 
-template <bool kApprox = false>
 __device__ __forceinline__ float lobe_f(float b, float d, float e, float f, float h) {
   const float mn4 = fminf(fminf(b, d), fminf(f, h)), mx4 = fmaxf(fmaxf(b, d), fmaxf(f, h));
-  const float hitMin = fminf(mn4, e) * rcp_f<kApprox>(4.0f * mx4);
-  const float hitMax = (1.0f - fmaxf(mx4, e)) * rcp_f<kApprox>(fmaf(4.0f, mn4, -4.0f));
+  const float hitMin = fminf(mn4, e) * rcp_f(4.0f * mx4);
+  const float hitMax = (1.0f - fmaxf(mx4, e)) * rcp_f(fmaf(4.0f, mn4, -4.0f));
   return fmaxf(-hitMin, hitMax);
 }
 
-template <bool kApprox = false>
 __device__ __forceinline__ void rcas_px(const RcasParams& p, PxF b, PxF d, PxF e, PxF f, PxF h, float4& out) {
-  const float lobe = fmaxf(-0.1875f, fminf(fmaxf(lobe_f<kApprox>(b.r, d.r, e.r, f.r, h.r),
-                                               fmaxf(lobe_f<kApprox>(b.g, d.g, e.g, f.g, h.g), lobe_f<kApprox>(b.b, d.b, e.b, f.b, h.b))), 0.0f)) * p.sharp;
+  const float lobe = fmaxf(-0.1875f, fminf(fmaxf(lobe_f(b.r, d.r, e.r, f.r, h.r),
+                                               fmaxf(lobe_f(b.g, d.g, e.g, f.g, h.g), lobe_f(b.b, d.b, e.b, f.b, h.b))), 0.0f)) * p.sharp;
   const float a = fmaf(4.0f, lobe, 1.0f);
   const float s = __uint_as_float(0x7ef19fffu - __float_as_uint(a));  // APrxMedRcpF1 (ffx_a.h:1844)
   const float rcpL = s * fmaf(-s, a, 2.0f);
@@ -75,7 +71,7 @@ __device__ __forceinline__ PxF shfl_px(PxF v, int delta_up) {
   return o;
 }
 
-template <bool kChecked, bool kApprox = false>
+template <bool kChecked>
 __device__ __forceinline__ void rcas_rows_f32(const RcasParams& p, int x, int ys, int lane) {
   const bool writer = lane >= 1 && lane <= 30 && (!kChecked || x < p.out.w);
   PairF rows[kFRows + 2];
@@ -88,8 +84,8 @@ __device__ __forceinline__ void rcas_rows_f32(const RcasParams& p, int x, int ys
     const PairF prev = rows[r], cur = rows[r + 1], next = rows[r + 2];
     const PxF left = shfl_px(cur.b, 1), right = shfl_px(cur.a, 0);  // left lane's pixel1, right lane's pixel0
     float4 o0, o1;
-    rcas_px<kApprox>(p, prev.a, left, cur.a, cur.b, next.a, o0);
-    rcas_px<kApprox>(p, prev.b, cur.a, cur.b, right, next.b, o1);
+    rcas_px(p, prev.a, left, cur.a, cur.b, next.a, o0);
+    rcas_px(p, prev.b, cur.a, cur.b, right, next.b, o1);
     if (writer) {
       float4* o = reinterpret_cast<float4*>(p.out.base + (long long)(y - p.out.row0) * p.out.pitch) + x;
       o[0] = o0;
@@ -98,15 +94,14 @@ __device__ __forceinline__ void rcas_rows_f32(const RcasParams& p, int x, int ys
   }
 }
 
-template <bool kApprox>
 __global__ void __launch_bounds__(32 * kFWarps) rcas_f32_packed_kernel(const RcasParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kFSpan - 2, x = x0 + lane * 2;
   const int ys = p.y0 + (blockIdx.y * kFWarps + warp) * kFRows;
   if (ys >= p.y1) return;
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kFRows < p.in.h && ys + kFRows <= p.y1;
-  if (interior) rcas_rows_f32<false, kApprox>(p, x, ys, lane);
-  else rcas_rows_f32<true, kApprox>(p, x, ys, lane);
+  if (interior) rcas_rows_f32<false>(p, x, ys, lane);
+  else rcas_rows_f32<true>(p, x, ys, lane);
 }
 
 #ifndef FSR1_CPU_EMU
@@ -115,14 +110,8 @@ cudaError_t launch_rcas_f32_packed(const RcasParams& p, cudaStream_t s, const ch
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
   const dim3 grid((p.out.w + kFSpan - 1) / kFSpan, (p.y1 - p.y0 + kFWarps * kFRows - 1) / (kFWarps * kFRows), 1);
-  static const int variant = env_knob("FSR1_RCAS_F32_VARIANT", 0);
-  if (variant == 1) {
-    rcas_f32_packed_kernel<true><<<grid, 32 * kFWarps, 0, s>>>(p);
-    *name = "rcas_f32_packed<2px,4rows,shfl60,mufu>";
-  } else {
-    rcas_f32_packed_kernel<false><<<grid, 32 * kFWarps, 0, s>>>(p);
-    *name = "rcas_f32_packed<2px,4rows,shfl60>";
-  }
+  rcas_f32_packed_kernel<<<grid, 32 * kFWarps, 0, s>>>(p);
+  *name = "rcas_f32_packed<2px,4rows,shfl60>";
   return cudaGetLastError();
 }
 

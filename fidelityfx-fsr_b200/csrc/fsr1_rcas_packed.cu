@@ -12,7 +12,7 @@
 //   * arithmetic is half2 over the lane's two pixels, structure-of-arrays like the reference's FsrRcasHx2
 //     (ffx_fsr1.h:888-984): (R0,R1) (G0,G1) (B0,B1).
 // Numerics: the six "high precision" reciprocals (ffx_fsr1.h:750-755) are rcp.approx.f32 on the unpacked
-// halves (h2rcp); the resolve reciprocal is the packed APrxMedRcpH2 (ffx_a.h:1815).  Against the fp32
+// halves (h2rcp, MUFU; a packed Newton iteration on the fp16 pipe measured slower); the resolve reciprocal is the packed APrxMedRcpH2 (ffx_a.h:1815).  Against the fp32
 // oracle on the same half input: <= 2e-3 (tolerance 1e-2).  min/max are the non-propagating half2 forms, so
 // the 0*inf NaNs of flat black / white neighbourhoods drop out exactly as with HLSL min/max (:756-759).
 #include <stdlib.h>
@@ -20,7 +20,8 @@
 
 namespace fsr1 {
 
-constexpr int kWarps = 8;   // warps per CTA of the 8-warp variants, stacked vertically: CTA = 60 x (kNW*kRows) output pixels (kRows = rows walked by one lane; default kNW = 4)
+constexpr int kNW = 4;     // warps per CTA, stacked vertically: CTA = 60 x (kNW*kRows) output pixels
+constexpr int kRows = 4;   // rows walked by one lane
 constexpr int kSpan = 60;   // output pixels per warp per row (lanes 1..30)
 
 struct Row3 { __half2 r, g, b; };  // (pixel0, pixel1) per channel
@@ -45,7 +46,7 @@ __device__ __forceinline__ Row3 load_pair(const RcasParams& p, int x, int y) {
   }
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if (kClamp) y = clampi(y, 0, p.in.h - 1);
-  if (y >= 0 && y < p.in.h) {
+  if (row_stored(p.in, y)) {  // rows outside the stored window are prefetched past the row range, never used
     const uint2* row = reinterpret_cast<const uint2*>(p.in.base + (long long)(y - p.in.row0) * p.in.pitch);
     if (x >= 0 && x + 1 < p.in.w) {
       v = __ldg(reinterpret_cast<const uint4*>(row + x));
@@ -60,25 +61,13 @@ __device__ __forceinline__ Row3 load_pair(const RcasParams& p, int x, int y) {
   return to_soa(v);
 }
 
-// 1/a for two non-negative halves.  kNewton: packed bit-trick seed (ffx_a.h:1815's magic) + two Newton steps on
-// the fp16 pipe (a == 0 overflows to +inf after the second step, exactly what the limiter logic needs);
-// otherwise rcp.approx.f32 on the unpacked halves (MUFU).
-template <bool kNewton> __device__ __forceinline__ __half2 rcp_pos(__half2 a) {
-  if (!kNewton) return h2rcp(a);
-  const __half2 two = __float2half2_rn(2.0f);
-  __half2 b = uh2(0x778d778du - hu2(a));
-  b = __hmul2(b, __hfma2(__hneg2(b), a, two));
-  return __hmul2(b, __hfma2(__hneg2(b), a, two));
-}
-
 // lobe of one channel for two pixels:  max(-hitMin, hitMax) = -min( min(mn4,e)/(4 mx4), (1-max(mx4,e))/(4-4 mn4) )
-template <bool kNewton>
 __device__ __forceinline__ __half2 lobe_channel(__half2 b, __half2 d, __half2 e, __half2 f, __half2 h) {
   const __half2 mn4 = __hmin2(__hmin2(b, d), __hmin2(f, h));
   const __half2 mx4 = __hmax2(__hmax2(b, d), __hmax2(f, h));
   const __half2 k4 = __float2half2_rn(4.0f), k1 = __float2half2_rn(1.0f), km4 = __float2half2_rn(-4.0f);
-  const __half2 hitMin = __hmul2(__hmin2(mn4, e), rcp_pos<kNewton>(__hmul2(k4, mx4)));
-  const __half2 negHitMax = __hmul2(__hsub2(k1, __hmax2(mx4, e)), rcp_pos<kNewton>(__hfma2(km4, mn4, k4)));
+  const __half2 hitMin = __hmul2(__hmin2(mn4, e), h2rcp(__hmul2(k4, mx4)));
+  const __half2 negHitMax = __hmul2(__hsub2(k1, __hmax2(mx4, e)), h2rcp(__hfma2(km4, mn4, k4)));
   return __hneg2(__hmin2(hitMin, negHitMax));  // __hmin2 drops the 0*inf NaN of a flat black / white ring
 }
 
@@ -88,7 +77,7 @@ __device__ __forceinline__ __half2 resolve_channel(__half2 lobe, __half2 rcpL, _
   return __hmul2(__hfma2(lobe, ring, e), rcpL);
 }
 
-template <bool kChecked, bool kClamp, bool kNewton, int kRows>
+template <bool kChecked, bool kClamp>
 __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, int lane) {
   const __half2 sharp = uh2(p.sharp_h2);
   const __half2 kLimit = __float2half2_rn(-0.1875f), kZero = __float2half2_rn(0.0f);
@@ -118,9 +107,9 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
     const __half2 fG = uh2(__byte_perm(hu2(cur.g), __shfl_down_sync(0xffffffffu, hu2(cur.g), 1), 0x5432));
     const __half2 fB = uh2(__byte_perm(hu2(cur.b), __shfl_down_sync(0xffffffffu, hu2(cur.b), 1), 0x5432));
 
-    const __half2 lR = lobe_channel<kNewton>(prev.r, dR, cur.r, fR, next.r);
-    const __half2 lG = lobe_channel<kNewton>(prev.g, dG, cur.g, fG, next.g);
-    const __half2 lB = lobe_channel<kNewton>(prev.b, dB, cur.b, fB, next.b);
+    const __half2 lR = lobe_channel(prev.r, dR, cur.r, fR, next.r);
+    const __half2 lG = lobe_channel(prev.g, dG, cur.g, fG, next.g);
+    const __half2 lB = lobe_channel(prev.b, dB, cur.b, fB, next.b);
     const __half2 lobe = __hmul2(__hmax2(kLimit, __hmin2(__hmax2(lR, __hmax2(lG, lB)), kZero)), sharp);
     // APrxMedRcpH2(4*lobe+1): packed 16-bit magic subtract (no borrow: both lanes' bits <= 0x3c00) + one Newton step
     const __half2 a = __hfma2(__float2half2_rn(4.0f), lobe, __float2half2_rn(1.0f));
@@ -143,7 +132,7 @@ __device__ __forceinline__ void rcas_rows(const RcasParams& p, int x, int ys, in
   }
 }
 
-template <bool kClamp, bool kNewton, int kRows, int kNW = kWarps>
+template <bool kClamp>
 __global__ void __launch_bounds__(32 * kNW) rcas_h_packed_kernel(const RcasParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kSpan - 2;  // even -> every lane's pair is 16-byte aligned
@@ -152,9 +141,9 @@ __global__ void __launch_bounds__(32 * kNW) rcas_h_packed_kernel(const RcasParam
   if (ys >= p.y1) return;  // whole warp
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kRows < p.in.h && ys + kRows <= p.y1;
   if (interior)
-    rcas_rows<false, kClamp, kNewton, kRows>(p, x, ys, lane);
+    rcas_rows<false, kClamp>(p, x, ys, lane);
   else
-    rcas_rows<true, kClamp, kNewton, kRows>(p, x, ys, lane);
+    rcas_rows<true, kClamp>(p, x, ys, lane);
 }
 
 // ---- RCAS for the UNORM formats (experimental, FSR1_UNORM_TILED=1) ---------------------------------------------------
@@ -194,7 +183,7 @@ template <int kBits> __device__ __forceinline__ uint2 encode_pair(__half2 r, __h
 template <bool kClamp> __device__ __forceinline__ uint2 load_words(const RcasParams& p, int x, int y) {
   uint2 v = make_uint2(0u, 0u);
   if (kClamp) y = clampi(y, 0, p.in.h - 1);
-  if (y >= 0 && y < p.in.h) {
+  if (row_stored(p.in, y)) {
     const uint32_t* row = reinterpret_cast<const uint32_t*>(p.in.base + (long long)(y - p.in.row0) * p.in.pitch);
     if (kClamp) {
       v.x = __ldg(row + clampi(x, 0, p.in.w - 1));
@@ -207,7 +196,7 @@ template <bool kClamp> __device__ __forceinline__ uint2 load_words(const RcasPar
   return v;
 }
 
-template <bool kChecked, bool kClamp, int kBits, int kRows>
+template <bool kChecked, bool kClamp, int kBits>
 __device__ __forceinline__ void rcas_rows_u(const RcasParams& p, int x, int ys, int lane) {
   const __half2 sharp = uh2(p.sharp_h2);
   const __half2 kLimit = __float2half2_rn(-0.1875f), kZero = __float2half2_rn(0.0f);
@@ -233,9 +222,9 @@ __device__ __forceinline__ void rcas_rows_u(const RcasParams& p, int x, int ys, 
     const __half2 fR = uh2(__byte_perm(hu2(cur.r), __shfl_down_sync(0xffffffffu, hu2(cur.r), 1), 0x5432));
     const __half2 fG = uh2(__byte_perm(hu2(cur.g), __shfl_down_sync(0xffffffffu, hu2(cur.g), 1), 0x5432));
     const __half2 fB = uh2(__byte_perm(hu2(cur.b), __shfl_down_sync(0xffffffffu, hu2(cur.b), 1), 0x5432));
-    const __half2 lR = lobe_channel<false>(prev.r, dR, cur.r, fR, next.r);
-    const __half2 lG = lobe_channel<false>(prev.g, dG, cur.g, fG, next.g);
-    const __half2 lB = lobe_channel<false>(prev.b, dB, cur.b, fB, next.b);
+    const __half2 lR = lobe_channel(prev.r, dR, cur.r, fR, next.r);
+    const __half2 lG = lobe_channel(prev.g, dG, cur.g, fG, next.g);
+    const __half2 lB = lobe_channel(prev.b, dB, cur.b, fB, next.b);
     const __half2 lobe = __hmul2(__hmax2(kLimit, __hmin2(__hmax2(lR, __hmax2(lG, lB)), kZero)), sharp);
     const __half2 a = __hfma2(__float2half2_rn(4.0f), lobe, __float2half2_rn(1.0f));
     const __half2 s = uh2(0x778d778du - hu2(a));
@@ -256,21 +245,19 @@ __device__ __forceinline__ void rcas_rows_u(const RcasParams& p, int x, int ys, 
 
 template <bool kClamp, int kBits>
 __global__ void __launch_bounds__(32 * 4) rcas_u_packed_kernel(const RcasParams p) {
-  constexpr int kNW = 4, kRows = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kSpan - 2;  // even -> every lane's pair is 8-byte aligned
   const int x = x0 + lane * 2;
   const int ys = p.y0 + (blockIdx.y * kNW + warp) * kRows;
   if (ys >= p.y1) return;  // whole warp
   const bool interior = x0 >= 0 && x0 + 64 <= p.in.w && ys >= 1 && ys + kRows < p.in.h && ys + kRows <= p.y1;
-  if (interior) rcas_rows_u<false, kClamp, kBits, kRows>(p, x, ys, lane);
-  else rcas_rows_u<true, kClamp, kBits, kRows>(p, x, ys, lane);
+  if (interior) rcas_rows_u<false, kClamp, kBits>(p, x, ys, lane);
+  else rcas_rows_u<true, kClamp, kBits>(p, x, ys, lane);
 }
 
 #ifndef FSR1_CPU_EMU  // tests/emu compiles the device code above for the host and supplies its own launcher
 cudaError_t launch_rcas_u_packed(const RcasParams& p, int format, cudaStream_t s, const char** name) {
-  static const int enabled = env_knob("FSR1_UNORM_TILED", 0);  // 1: R8G8B8A8 only, 2: also R10G10B10A2 (coarser than its codes)
-  if (!(enabled >= 1 && format == 3) && !(enabled >= 2 && format == 4)) return cudaErrorNotSupported;
+  if (format != 3 && format != 4) return cudaErrorNotSupported;
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 7) || (p.in.pitch & 7) || (reinterpret_cast<uintptr_t>(p.out.base) & 7) || (p.out.pitch & 7))
     return cudaErrorNotSupported;
   const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + 15) / 16, 1);
@@ -290,29 +277,13 @@ cudaError_t launch_rcas_h_packed(const RcasParams& p, cudaStream_t s, const char
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || (reinterpret_cast<uintptr_t>(p.out.base) & 15) ||
       (p.out.pitch & 15))
     return cudaErrorNotSupported;
-  // development knob: FSR1_RCAS_VARIANT = 0 (8-warp CTAs, 4 rows/lane, MUFU), 1 (4 rows, Newton), 2 (8 rows/lane, MUFU),
-  // 3 = default (as 0 with 4-warp CTAs: same kernel time, but the smaller CTA starts earlier in the tail of the
-  // preceding EASU and shares SMs with it when frames are pipelined: 92.1 -> 90.7 us per frame back to back)
-  static const int variant = env_knob("FSR1_RCAS_VARIANT", 3);
-  const int rows_per_cta = (variant == 3 ? 4 : kWarps) * (variant == 2 ? 8 : 4);
-  const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + rows_per_cta - 1) / rows_per_cta, 1);
-  if (variant == 3) {
-    if (p.clamp) rcas_h_packed_kernel<true, false, 4, 4><<<grid, 32 * 4, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, false, 4, 4><<<grid, 32 * 4, 0, s>>>(p);
-    *name = "rcas_h_packed<2px,4rows,shfl60,mufu>";
-  } else if (variant == 1) {
-    if (p.clamp) rcas_h_packed_kernel<true, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, true, 4><<<grid, 32 * kWarps, 0, s>>>(p);
-    *name = "rcas_h_packed<2px,4rows,shfl60,newton>";
-  } else if (variant == 2) {
-    if (p.clamp) rcas_h_packed_kernel<true, false, 8><<<grid, 32 * kWarps, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, false, 8><<<grid, 32 * kWarps, 0, s>>>(p);
-    *name = "rcas_h_packed<2px,8rows,shfl60,mufu>";
-  } else {
-    if (p.clamp) rcas_h_packed_kernel<true, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
-    else rcas_h_packed_kernel<false, false, 4><<<grid, 32 * kWarps, 0, s>>>(p);
-    *name = "rcas_h_packed<2px,4rows,shfl60,mufu,8w>";
-  }
+  // 4-warp CTAs (60 x 16 pixels), 4 rows per lane, MUFU reciprocals: same kernel time as 8-warp CTAs, but the smaller
+  // CTA starts earlier in the tail of the preceding EASU and shares SMs with it when frames are pipelined
+  // (round 1: 92.1 -> 90.7 us per frame back to back; the 8-row and Newton-reciprocal variants measured slower)
+  const dim3 grid((p.out.w + kSpan - 1) / kSpan, (p.y1 - p.y0 + kNW * kRows - 1) / (kNW * kRows), 1);
+  if (p.clamp) rcas_h_packed_kernel<true><<<grid, 32 * kNW, 0, s>>>(p);
+  else rcas_h_packed_kernel<false><<<grid, 32 * kNW, 0, s>>>(p);
+  *name = "rcas_h_packed<2px,4rows,shfl60>";
   return cudaGetLastError();
 }
 

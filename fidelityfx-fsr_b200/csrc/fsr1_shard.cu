@@ -1,0 +1,443 @@
+// fsr1_shard.cu — row-slab sharding of the EASU+RCAS path across the GPUs of one box, with the EASU input halo
+// moved by DIRECT NVLink stores into the neighbour's memory (SURVEY.md §8(e) "Alternative": P2P mapped slabs).
+//
+// The reference has no multi-GPU path (sample/src/DX12/FSRSample.cpp:901 is a comment); this is new.  One fsr1_shard
+// per rank (= per GPU; ranks may be processes, attached through CUDA IPC handles, or live in one process, attached
+// by pointer).  The OUTPUT image is cut into `world` row slabs; rank k owns input rows [k inH/world, (k+1) inH/world)
+// and needs 2-3 more rows each side (the EASU footprint of its slab plus the one-row apron RCAS reads).
+//
+// Data plane per frame (no NCCL, no host round trip, no collective):
+//   comm stream   halo_push_kernel: block 0 copies my top rows into the upper neighbour's window (its bottom halo),
+//                 block 1 my bottom rows into the lower neighbour's; 128-bit stores over NVLink, __threadfence_system,
+//                 then a release store of the frame's sequence number into the neighbour's `ready` flag.
+//   EASU stream   halo_wait_kernel (2 lanes spin on MY `ready` flags, acquire loads of local memory) -> EASU over the
+//                 slab +-1 row -> credit_signal_kernel (release store of the sequence number into the neighbours'
+//                 `credit` flags: "your rows in my window may be overwritten").
+//   RCAS stream   RCAS of frame i overlaps EASU of frame i+1 exactly as api.FramePipeline does on one GPU.
+// Flow control is by sequence numbers in device memory, so it is independent of host timing on either side: a push
+// for the q-th use of a slot waits for credit q-1, EASU of use q waits for ready q.  Every spin is bounded (a wall
+// clock timeout sets an error word instead of hanging the GPU).
+#include <new>
+#include <string.h>
+
+#include "../../include/fsr1_b200.h"
+#include "fsr1_common.cuh"
+
+namespace {
+
+constexpr uint32_t kFlagBytes = 4096;          // flags page at the start of the arena
+constexpr uint32_t kMaxSlots = 128;
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s
+
+enum { kFromUp = 0, kFromDown = 1 };
+// flag word index inside an arena's flags page
+__host__ __device__ inline uint32_t ready_idx(uint32_t slot, int from) { return slot * 4 + from; }
+__host__ __device__ inline uint32_t credit_idx(uint32_t slot, int from) { return slot * 4 + 2 + from; }
+constexpr uint32_t kStatusIdx = kMaxSlots * 4;  // != 0: a spin timed out (value = 1 + which)
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *flag >= want (sequence numbers, wrap-safe); false on timeout
+__device__ bool spin_until(const uint32_t* flag, uint32_t want) {
+  if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
+  const unsigned long long t0 = global_ns();
+  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+    if (global_ns() - t0 > kSpinTimeoutNs) return false;
+    __nanosleep(50);
+  }
+  return true;
+}
+
+struct PushSide {
+  const uint4* src;        // my rows (local)
+  uint4* dst;              // the neighbour's window rows (peer memory); nullptr = no neighbour on this side
+  uint32_t n16;            // 16-byte units
+  const uint32_t* credit;  // local: the neighbour has finished reading the previous use of this slot
+  uint32_t* ready;         // peer: "your halo rows for use q are in place"
+};
+
+__global__ void __launch_bounds__(1024) halo_push_kernel(const PushSide up, const PushSide down, const uint32_t q, uint32_t* status) {
+  const PushSide s = blockIdx.x == 0 ? up : down;
+  if (!s.dst) return;
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = spin_until(s.credit, q - 1) ? 1 : 0;
+    if (!ok) atomicExch(status, 1u + blockIdx.x);
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (uint32_t i = threadIdx.x; i < s.n16; i += blockDim.x) s.dst[i] = s.src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(s.ready, q);
+}
+
+__global__ void halo_wait_kernel(const uint32_t* ready_up, const uint32_t* ready_down, const uint32_t q, uint32_t* status) {
+  const uint32_t* f = threadIdx.x == 0 ? ready_up : (threadIdx.x == 1 ? ready_down : nullptr);
+  if (f && !spin_until(f, q)) atomicExch(status, 3u + threadIdx.x);
+}
+
+__global__ void credit_signal_kernel(uint32_t* credit_up, uint32_t* credit_down, const uint32_t q) {
+  uint32_t* f = threadIdx.x == 0 ? credit_up : (threadIdx.x == 1 ? credit_down : nullptr);
+  if (f) st_release_sys(f, q);
+}
+
+int bpp_of(uint32_t fmt) {
+  switch (fmt) {
+    case FSR1_FORMAT_RGBA16F: return 8;
+    case FSR1_FORMAT_RGBA32F: return 16;
+    case FSR1_FORMAT_RGBA8_UNORM: case FSR1_FORMAT_RGB10A2_UNORM: return 4;
+    default: return 0;
+  }
+}
+
+struct Rows { uint32_t a, b; };  // [a, b)
+
+}  // namespace
+
+struct fsr1_shard {
+  uint32_t in_w, in_h, out_w, out_h, format, world, rank, slots, flags;
+  int device;
+  uint32_t econ[16], rcon[4];
+  // geometry of THIS rank
+  Rows out_rows, easu_rows, owned, needed, window;
+  // arena: [flags page][slot 0 window][slot 1 window]...; identical layout on every rank
+  uint64_t pitch, slot_stride, arena_bytes;
+  uint32_t win_rows_max;
+  unsigned char* arena;
+  unsigned char* peer[2];      // [kFromUp] = arena of rank-1, [kFromDown] = arena of rank+1 (mapped), nullptr = none
+  bool peer_is_ipc[2];
+  uint32_t peer_win0[2];       // first logical row of the neighbour's window
+  Rows send[2];                // my rows the neighbour needs
+  unsigned char* tmp;          // slots x rows easu_rows
+  unsigned char* out;          // slots x rows out_rows
+  uint64_t out_pitch, tmp_slot_stride, out_slot_stride;
+  uint32_t seq[kMaxSlots];
+  cudaStream_t s_comm, s_easu, s_rcas;
+  cudaEvent_t ev_in[kMaxSlots], ev_push[kMaxSlots], ev_easu[kMaxSlots], ev_rcas[kMaxSlots];
+  bool attached;
+};
+
+namespace {
+
+Rows plan_out_rows(const fsr1_shard* s, uint32_t r) {
+  return Rows{(uint32_t)((uint64_t)r * s->out_h / s->world), (uint32_t)((uint64_t)(r + 1) * s->out_h / s->world)};
+}
+Rows plan_easu_rows(const fsr1_shard* s, uint32_t r) {
+  const Rows o = plan_out_rows(s, r);
+  return Rows{o.a == 0 ? 0 : o.a - 1, o.b >= s->out_h ? s->out_h : o.b + 1};
+}
+Rows plan_owned(const fsr1_shard* s, uint32_t r) {
+  return Rows{(uint32_t)((uint64_t)r * s->in_h / s->world), (uint32_t)((uint64_t)(r + 1) * s->in_h / s->world)};
+}
+Rows plan_needed(const fsr1_shard* s, uint32_t r) {
+  const Rows e = plan_easu_rows(s, r);
+  uint32_t first = 0, last = 0;
+  fsr1_easu_input_rows(s->econ, s->in_h, e.a, e.b, &first, &last);
+  return Rows{first, last + 1};
+}
+Rows plan_window(const fsr1_shard* s, uint32_t r) {
+  const Rows o = plan_owned(s, r), n = plan_needed(s, r);
+  return Rows{o.a < n.a ? o.a : n.a, o.b > n.b ? o.b : n.b};
+}
+
+int cuda_rc(cudaError_t e) { return e == cudaSuccess ? FSR1_OK : FSR1_ERR_CUDA; }
+
+struct DeviceGuard {  // calls may come from a thread whose current device is another GPU (one process, several ranks)
+  int prev;
+  explicit DeviceGuard(int dev) : prev(-1) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_t out_w, uint32_t out_h, uint32_t format,
+                      uint32_t world, uint32_t rank, uint32_t slots, float sharpness_stops, uint32_t flags) {
+  if (!out_sh || !in_w || !in_h || !out_w || !out_h || !world || rank >= world || !slots || slots > kMaxSlots) return FSR1_ERR_INVALID_ARGUMENT;
+  const int bpp = bpp_of(format);
+  if (!bpp) return FSR1_ERR_INVALID_ARGUMENT;
+  if (world > in_h || world > out_h) return FSR1_ERR_INVALID_ARGUMENT;  // no empty slabs
+  fsr1_shard* s = new (std::nothrow) fsr1_shard();
+  if (!s) return FSR1_ERR_INVALID_ARGUMENT;
+  memset(s, 0, sizeof *s);
+  s->in_w = in_w; s->in_h = in_h; s->out_w = out_w; s->out_h = out_h; s->format = format;
+  s->world = world; s->rank = rank; s->slots = slots; s->flags = flags;
+  if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return FSR1_ERR_NO_DEVICE; }
+  fsr1_easu_con(s->econ, (float)in_w, (float)in_h, (float)in_w, (float)in_h, (float)out_w, (float)out_h);
+  fsr1_rcas_con(s->rcon, sharpness_stops);
+  s->out_rows = plan_out_rows(s, rank);
+  s->easu_rows = plan_easu_rows(s, rank);
+  s->owned = plan_owned(s, rank);
+  s->needed = plan_needed(s, rank);
+  s->window = plan_window(s, rank);
+  // every rank's halo must come from its direct neighbours only (true whenever a slab is taller than the halo)
+  s->win_rows_max = 0;
+  for (uint32_t r = 0; r < world; r++) {
+    const Rows n = plan_needed(s, r), w = plan_window(s, r);
+    const uint32_t lo = r == 0 ? 0 : plan_owned(s, r - 1).a, hi = r + 1 == world ? in_h : plan_owned(s, r + 1).b;
+    if (n.a < lo || n.b > hi) { delete s; return FSR1_ERR_UNSUPPORTED; }
+    if (w.b - w.a > s->win_rows_max) s->win_rows_max = w.b - w.a;
+  }
+  for (int side = 0; side < 2; side++) {
+    const bool has = side == kFromUp ? rank > 0 : rank + 1 < world;
+    s->send[side] = Rows{0, 0};
+    if (!has) continue;
+    const uint32_t peer = side == kFromUp ? rank - 1 : rank + 1;
+    const Rows pn = plan_needed(s, peer);
+    const uint32_t a = s->owned.a > pn.a ? s->owned.a : pn.a, b = s->owned.b < pn.b ? s->owned.b : pn.b;
+    if (b > a) s->send[side] = Rows{a, b};
+    s->peer_win0[side] = plan_window(s, peer).a;
+  }
+  s->pitch = ((uint64_t)in_w * bpp + 127) & ~(uint64_t)127;
+  s->slot_stride = ((uint64_t)s->win_rows_max * s->pitch + 255) & ~(uint64_t)255;
+  s->arena_bytes = kFlagBytes + s->slot_stride * slots;
+  s->out_pitch = ((uint64_t)out_w * bpp + 127) & ~(uint64_t)127;
+  s->tmp_slot_stride = (uint64_t)(s->easu_rows.b - s->easu_rows.a) * s->out_pitch;
+  s->out_slot_stride = (uint64_t)(s->out_rows.b - s->out_rows.a) * s->out_pitch;
+  cudaError_t e;
+  // cudaMalloc (not a pool / VMM allocation): the arena must be exportable through cudaIpcGetMemHandle
+  if ((e = cudaMalloc((void**)&s->arena, s->arena_bytes)) != cudaSuccess || (e = cudaMemset(s->arena, 0, s->arena_bytes)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&s->tmp, s->tmp_slot_stride * slots)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&s->out, s->out_slot_stride * slots)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&s->s_easu, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&s->s_rcas, cudaStreamNonBlocking)) != cudaSuccess) {
+    fsr1_shard_destroy(s);
+    return FSR1_ERR_CUDA;
+  }
+  for (uint32_t i = 0; i < slots; i++) {
+    if (cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_push[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_easu[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_rcas[i], cudaEventDisableTiming) != cudaSuccess) {
+      fsr1_shard_destroy(s);
+      return FSR1_ERR_CUDA;
+    }
+  }
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) { fsr1_shard_destroy(s); return FSR1_ERR_CUDA; }  // flags are zero before anyone attaches
+  s->attached = world == 1;
+  *out_sh = s;
+  return FSR1_OK;
+}
+
+void fsr1_shard_destroy(fsr1_shard* s) {
+  if (!s) return;
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  for (int side = 0; side < 2; side++)
+    if (s->peer[side] && s->peer_is_ipc[side]) cudaIpcCloseMemHandle(s->peer[side]);
+  for (uint32_t i = 0; i < s->slots && i < kMaxSlots; i++) {
+    if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+    if (s->ev_push[i]) cudaEventDestroy(s->ev_push[i]);
+    if (s->ev_easu[i]) cudaEventDestroy(s->ev_easu[i]);
+    if (s->ev_rcas[i]) cudaEventDestroy(s->ev_rcas[i]);
+  }
+  if (s->s_comm) cudaStreamDestroy(s->s_comm);
+  if (s->s_easu) cudaStreamDestroy(s->s_easu);
+  if (s->s_rcas) cudaStreamDestroy(s->s_rcas);
+  cudaFree(s->arena);
+  cudaFree(s->tmp);
+  cudaFree(s->out);
+  delete s;
+}
+
+int fsr1_shard_geometry(const fsr1_shard* s, fsr1_shard_info* info) {
+  if (!s || !info) return FSR1_ERR_INVALID_ARGUMENT;
+  info->out_row0 = s->out_rows.a; info->out_row1 = s->out_rows.b;
+  info->easu_row0 = s->easu_rows.a; info->easu_row1 = s->easu_rows.b;
+  info->owned_row0 = s->owned.a; info->owned_row1 = s->owned.b;
+  info->needed_row0 = s->needed.a; info->needed_row1 = s->needed.b;
+  info->window_row0 = s->window.a; info->window_row1 = s->window.b;
+  info->send_up_row0 = s->send[kFromUp].a; info->send_up_row1 = s->send[kFromUp].b;
+  info->send_down_row0 = s->send[kFromDown].a; info->send_down_row1 = s->send[kFromDown].b;
+  info->halo_recv_bytes = (uint64_t)((s->owned.a - s->window.a) + (s->window.b - s->owned.b)) * s->in_w * bpp_of(s->format);
+  info->arena_bytes = s->arena_bytes;
+  return FSR1_OK;
+}
+
+int fsr1_shard_export(const fsr1_shard* s, void* handle) {
+  if (!s || !handle) return FSR1_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == FSR1_SHARD_HANDLE_BYTES, "handle size");
+  DeviceGuard g(s->device);
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, s->arena) != cudaSuccess) return FSR1_ERR_CUDA;
+  memcpy(handle, &h, sizeof h);
+  return FSR1_OK;
+}
+
+void* fsr1_shard_arena(const fsr1_shard* s) { return s ? s->arena : nullptr; }
+
+static int attach_done(fsr1_shard* s) {
+  s->attached = (s->rank == 0 || s->peer[kFromUp]) && (s->rank + 1 == s->world || s->peer[kFromDown]);
+  return s->attached ? FSR1_OK : FSR1_ERR_INVALID_ARGUMENT;
+}
+
+int fsr1_shard_attach(fsr1_shard* s, const void* handles, uint32_t count) {
+  if (!s || !handles || count != s->world) return FSR1_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  for (int side = 0; side < 2; side++) {
+    const bool has = side == kFromUp ? s->rank > 0 : s->rank + 1 < s->world;
+    if (!has || s->peer[side]) continue;
+    const uint32_t peer = side == kFromUp ? s->rank - 1 : s->rank + 1;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char*)handles + (size_t)peer * FSR1_SHARD_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return FSR1_ERR_CUDA;
+    s->peer[side] = (unsigned char*)p;
+    s->peer_is_ipc[side] = true;
+  }
+  return attach_done(s);
+}
+
+int fsr1_shard_attach_local(fsr1_shard* s, fsr1_shard* up, fsr1_shard* down) {
+  if (!s) return FSR1_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  fsr1_shard* nb[2] = {up, down};
+  for (int side = 0; side < 2; side++) {
+    const bool has = side == kFromUp ? s->rank > 0 : s->rank + 1 < s->world;
+    if (!has) continue;
+    fsr1_shard* n = nb[side];
+    if (!n || n->world != s->world || n->rank != (side == kFromUp ? s->rank - 1 : s->rank + 1) || n->arena_bytes != s->arena_bytes)
+      return FSR1_ERR_INVALID_ARGUMENT;
+    if (n->device != s->device) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, s->device, n->device) != cudaSuccess || !can) return FSR1_ERR_UNSUPPORTED;
+      cudaError_t e = cudaDeviceEnablePeerAccess(n->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return FSR1_ERR_CUDA;
+    }
+    s->peer[side] = n->arena;
+    s->peer_is_ipc[side] = false;
+  }
+  return attach_done(s);
+}
+
+static fsr1_image make_img(void* data, uint64_t pitch, uint32_t w, uint32_t h, uint32_t row0, uint32_t rows, uint32_t fmt) {
+  fsr1_image im;
+  im.data = data; im.pitch_bytes = pitch; im.width = w; im.height = h; im.row0 = row0; im.rows = rows; im.format = fmt; im.reserved = 0;
+  return im;
+}
+static unsigned char* window_of(const fsr1_shard* s, unsigned char* arena, uint32_t slot) { return arena + kFlagBytes + (uint64_t)slot * s->slot_stride; }
+
+int fsr1_shard_input(const fsr1_shard* s, uint32_t slot, fsr1_image* owned) {
+  if (!s || !owned || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  *owned = make_img(window_of(s, s->arena, slot) + (uint64_t)(s->owned.a - s->window.a) * s->pitch, s->pitch, s->in_w, s->in_h, s->owned.a,
+                    s->owned.b - s->owned.a, s->format);
+  return FSR1_OK;
+}
+
+int fsr1_shard_window(const fsr1_shard* s, uint32_t slot, fsr1_image* window) {
+  if (!s || !window || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  *window = make_img(window_of(s, s->arena, slot), s->pitch, s->in_w, s->in_h, s->window.a, s->window.b - s->window.a, s->format);
+  return FSR1_OK;
+}
+
+int fsr1_shard_output(const fsr1_shard* s, uint32_t slot, fsr1_image* out) {
+  if (!s || !out || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  *out = make_img(s->out + (uint64_t)slot * s->out_slot_stride, s->out_pitch, s->out_w, s->out_h, s->out_rows.a, s->out_rows.b - s->out_rows.a,
+                  s->format);
+  return FSR1_OK;
+}
+
+int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
+  if (!s || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!s->attached) return FSR1_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  const bool one_stream = (s->flags & FSR1_SHARD_ONE_STREAM) != 0;
+  cudaStream_t se = s->s_easu, sr = one_stream ? s->s_easu : s->s_rcas;
+  const uint32_t q = ++s->seq[slot];
+  uint32_t* flags = reinterpret_cast<uint32_t*>(s->arena);
+  cudaError_t e;
+  if ((e = cudaEventRecord(s->ev_in[slot], caller)) != cudaSuccess) return cuda_rc(e);
+  const bool skip_halo = (s->flags & FSR1_SHARD_SKIP_HALO) != 0;  // measurement only: what the frame costs without the exchange
+  const bool up = s->rank > 0 && !skip_halo, down = s->rank + 1 < s->world && !skip_halo;
+  if (up || down) {
+    PushSide ps[2];
+    for (int side = 0; side < 2; side++) {
+      ps[side] = PushSide{nullptr, nullptr, 0, nullptr, nullptr};
+      const bool has = side == kFromUp ? up : down;
+      if (!has) continue;
+      const Rows r = s->send[side];
+      uint32_t* pf = reinterpret_cast<uint32_t*>(s->peer[side]);
+      ps[side].src = reinterpret_cast<const uint4*>(window_of(s, s->arena, slot) + (uint64_t)(r.a - s->window.a) * s->pitch);
+      ps[side].dst = reinterpret_cast<uint4*>(window_of(s, s->peer[side], slot) + (uint64_t)(r.a - s->peer_win0[side]) * s->pitch);
+      ps[side].n16 = (uint32_t)((uint64_t)(r.b - r.a) * s->pitch / 16);
+      ps[side].credit = flags + credit_idx(slot, side);
+      // I am the neighbour's lower (upper) peer when I push up (down)
+      ps[side].ready = pf + ready_idx(slot, side == kFromUp ? kFromDown : kFromUp);
+    }
+    if ((e = cudaStreamWaitEvent(s->s_comm, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
+    halo_push_kernel<<<2, 1024, 0, s->s_comm>>>(ps[kFromUp], ps[kFromDown], q, flags + kStatusIdx);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    if ((e = cudaEventRecord(s->ev_push[slot], s->s_comm)) != cudaSuccess) return cuda_rc(e);
+  }
+  if ((e = cudaStreamWaitEvent(se, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
+  if (q > 1 && !one_stream && (e = cudaStreamWaitEvent(se, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);  // the slot's intermediate is free
+  if (up || down) {
+    halo_wait_kernel<<<1, 32, 0, se>>>(up ? flags + ready_idx(slot, kFromUp) : nullptr, down ? flags + ready_idx(slot, kFromDown) : nullptr, q,
+                                       flags + kStatusIdx);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+  }
+  fsr1_image win, out;
+  fsr1_shard_window(s, slot, &win);
+  fsr1_shard_output(s, slot, &out);
+  fsr1_image tmp = make_img(s->tmp + (uint64_t)slot * s->tmp_slot_stride, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a,
+                            s->easu_rows.b - s->easu_rows.a, s->format);
+  const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+  int rc = fsr1_easu(&win, &tmp, s->econ, s->easu_rows.a, s->easu_rows.b, kflags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, se);
+  if (rc != FSR1_OK) return rc;
+  if (up || down) {
+    uint32_t* cu = up ? reinterpret_cast<uint32_t*>(s->peer[kFromUp]) + credit_idx(slot, kFromDown) : nullptr;
+    uint32_t* cd = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
+    credit_signal_kernel<<<1, 32, 0, se>>>(cu, cd, q);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+  }
+  if (!one_stream) {
+    if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
+    if ((e = cudaStreamWaitEvent(sr, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
+  }
+  rc = fsr1_rcas(&tmp, &out, s->rcon, s->out_rows.a, s->out_rows.b, kflags, sr);
+  if (rc != FSR1_OK) return rc;
+  if ((e = cudaEventRecord(s->ev_rcas[slot], sr)) != cudaSuccess) return cuda_rc(e);
+  return FSR1_OK;
+}
+
+int fsr1_shard_wait(fsr1_shard* s, uint32_t slot, void* stream) {
+  if (!s || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  if (s->seq[slot] == 0) return FSR1_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = cudaStreamWaitEvent(caller, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);
+  if (s->world > 1 && !(s->flags & FSR1_SHARD_SKIP_HALO) && (e = cudaStreamWaitEvent(caller, s->ev_push[slot], 0)) != cudaSuccess)
+    return cuda_rc(e);  // my rows have left
+  return FSR1_OK;
+}
+
+int fsr1_shard_status(fsr1_shard* s) {
+  if (!s) return FSR1_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  uint32_t st = 0;
+  if (cudaMemcpy(&st, reinterpret_cast<uint32_t*>(s->arena) + kStatusIdx, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return FSR1_ERR_CUDA;
+  return st == 0 ? FSR1_OK : FSR1_ERR_TIMEOUT;
+}
+
+}  // extern "C"

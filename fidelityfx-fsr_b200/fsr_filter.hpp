@@ -53,8 +53,10 @@ class FSR_Filter {
       throw std::runtime_error("FSR_Filter: only the FSR 1.0 path is implemented (no bilinear comparison mode)");
     // hdr = the sample's Sample.x (FSR_Filter.cpp:107,125): the last pass squares its output
     const uint32_t flags = (pState->bUseRcas ? 0u : FSR1_FLAG_NO_RCAS) | (hdr ? FSR1_FLAG_OUTPUT_SQUARE : 0u);
-    check(fsr1_context_upscale(m_ctx, input.data, input.pitchBytes, output.data, output.pitchBytes,
-                               pState->rcasAttenuation, flags, stream));
+    // the constants are rebuilt from THIS frame's render size, as the reference does on every call (FSR_Filter.cpp:106)
+    if (pState->renderWidth <= 0 || pState->renderHeight <= 0) throw std::runtime_error("FSR_Filter: pState->renderWidth/renderHeight not set");
+    check(fsr1_context_upscale_render(m_ctx, input.data, input.pitchBytes, (uint32_t)pState->renderWidth, (uint32_t)pState->renderHeight,
+                                      output.data, output.pitchBytes, pState->rcasAttenuation, flags, stream));
   }
 
  private:

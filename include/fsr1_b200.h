@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FSR1_ABI_VERSION 2
+#define FSR1_ABI_VERSION 3
 
 enum {
   FSR1_OK = 0,
@@ -51,7 +51,8 @@ enum {
   FSR1_ERR_UNSUPPORTED = -2,      /* format combination the kernels do not implement              */
   FSR1_ERR_WINDOW = -3,           /* an image window (row0/rows) does not hold the rows the pass reads/writes */
   FSR1_ERR_CUDA = -4,             /* a CUDA call failed; see fsr1_last_cuda_error()                */
-  FSR1_ERR_NO_DEVICE = -5         /* no usable sm_100 device / driver                              */
+  FSR1_ERR_NO_DEVICE = -5,        /* no usable sm_100 device / driver                              */
+  FSR1_ERR_TIMEOUT = -6           /* fsr1_shard_*: a neighbour's halo or credit did not arrive in time */
 };
 
 enum {
@@ -123,9 +124,64 @@ void fsr1_context_destroy(fsr1_context* ctx);
 int fsr1_context_upscale(fsr1_context* ctx, const void* in_dev, uint64_t in_pitch, void* out_dev, uint64_t out_pitch,
                          float sharpness_stops, uint32_t flags, void* stream);
 
+/* The same with the render size of THIS frame (dynamic resolution / a preset change without re-creating the resources):
+ * FSR_Filter::Upscale rebuilds FsrEasuCon from pState->renderWidth/renderHeight on every call (FSR_Filter.cpp:106). */
+int fsr1_context_upscale_render(fsr1_context* ctx, const void* in_dev, uint64_t in_pitch, uint32_t render_width,
+                                uint32_t render_height, void* out_dev, uint64_t out_pitch, float sharpness_stops,
+                                uint32_t flags, void* stream);
+
 /* Host-resident frames (pinned memory recommended): H2D copy, EASU, RCAS, D2H copy on `stream`. */
 int fsr1_context_upscale_host(fsr1_context* ctx, const void* in_host, uint64_t in_pitch, void* out_host,
                               uint64_t out_pitch, float sharpness_stops, uint32_t flags, void* stream);
+
+/* ---- row-slab sharding across the GPUs of one box (the reference has no multi-GPU path: new) ------
+ * The output image is cut into `world` contiguous row slabs, one per rank (= per GPU).  Rank k owns input rows
+ * [k*in_h/world, (k+1)*in_h/world) and needs 2-3 more rows each side: the EASU footprint of its slab plus the
+ * one-row apron RCAS reads, so there is exactly ONE neighbour exchange per frame and no collective.
+ * A fsr1_shard owns the rank's share of a ring of `slots` frames: input window (own rows + halo), intermediate,
+ * output slab, three internal streams.  The halo moves by direct NVLink stores into the neighbour's window
+ * (CUDA IPC between processes, peer access inside one process), flow-controlled by sequence numbers in device
+ * memory: no NCCL call, no host synchronisation and no allocation per frame.  Per frame the caller writes its
+ * input rows into fsr1_shard_input(slot) on `stream`, calls fsr1_shard_submit(slot, stream), and orders its
+ * consumer after fsr1_shard_wait(slot, stream).  RCAS of frame i overlaps EASU of frame i+1 on every rank.
+ * All ranks must create shards with identical arguments (except rank) and submit slots in the same order.
+ * Set-up between processes: every rank calls fsr1_shard_export, the 64-byte handles are gathered in rank order by
+ * any means (torch.distributed all_gather, MPI, a pipe), every rank calls fsr1_shard_attach.  In one process
+ * driving several devices: fsr1_shard_attach_local(shard, shard_of_rank-1, shard_of_rank+1). */
+typedef struct fsr1_shard fsr1_shard;
+#define FSR1_SHARD_HANDLE_BYTES 64
+#define FSR1_SHARD_ONE_STREAM (1u << 16) /* fsr1_shard_create flag: EASU and RCAS of a frame on one stream (no frame overlap) */
+#define FSR1_SHARD_SKIP_HALO (1u << 17)  /* MEASUREMENT ONLY: no halo exchange (slab borders are wrong); times the frame without it */
+
+typedef struct fsr1_shard_info {   /* logical row ranges [row0, row1) of this rank */
+  uint32_t out_row0, out_row1;       /* output slab                                                 */
+  uint32_t easu_row0, easu_row1;     /* rows EASU produces (slab + RCAS apron)                      */
+  uint32_t owned_row0, owned_row1;   /* input rows this rank owns (the caller writes them)          */
+  uint32_t needed_row0, needed_row1; /* input rows EASU reads                                       */
+  uint32_t window_row0, window_row1; /* input rows resident on this rank (owned + halo)             */
+  uint32_t send_up_row0, send_up_row1, send_down_row0, send_down_row1; /* rows pushed to rank-1 / rank+1 */
+  uint64_t halo_recv_bytes;          /* halo payload received per frame                             */
+  uint64_t arena_bytes;
+} fsr1_shard_info;
+
+/* `flags`: FSR1_FLAG_* for the kernels, optionally FSR1_SHARD_ONE_STREAM.  FSR1_ERR_UNSUPPORTED when a slab is
+ * shorter than the halo it must supply (the halo would come from beyond the direct neighbours). */
+int fsr1_shard_create(fsr1_shard** shard, uint32_t in_width, uint32_t in_height, uint32_t out_width, uint32_t out_height,
+                      uint32_t format, uint32_t world, uint32_t rank, uint32_t slots, float sharpness_stops, uint32_t flags);
+void fsr1_shard_destroy(fsr1_shard* shard);
+int fsr1_shard_geometry(const fsr1_shard* shard, fsr1_shard_info* info);
+int fsr1_shard_export(const fsr1_shard* shard, void* handle /* FSR1_SHARD_HANDLE_BYTES */);
+int fsr1_shard_attach(fsr1_shard* shard, const void* handles /* world x FSR1_SHARD_HANDLE_BYTES, rank order */, uint32_t count);
+int fsr1_shard_attach_local(fsr1_shard* shard, fsr1_shard* up /* rank-1 or NULL */, fsr1_shard* down /* rank+1 or NULL */);
+int fsr1_shard_input(const fsr1_shard* shard, uint32_t slot, fsr1_image* owned);   /* where the caller writes its rows */
+int fsr1_shard_window(const fsr1_shard* shard, uint32_t slot, fsr1_image* window); /* owned rows + halo (read-only)     */
+int fsr1_shard_output(const fsr1_shard* shard, uint32_t slot, fsr1_image* out);    /* the rank's output slab            */
+void* fsr1_shard_arena(const fsr1_shard* shard);
+/* Upscale the frame in `slot`: ordered after everything already on `stream`; returns without waiting. */
+int fsr1_shard_submit(fsr1_shard* shard, uint32_t slot, void* stream);
+/* Orders `stream` after the slot's result (and after this rank's halo rows have left: the input may be rewritten). */
+int fsr1_shard_wait(fsr1_shard* shard, uint32_t slot, void* stream);
+int fsr1_shard_status(fsr1_shard* shard);  /* FSR1_OK, or FSR1_ERR_TIMEOUT if a neighbour never answered (call after a sync) */
 
 /* ---- pointwise companions of the scaling path (ffx-fsr/ffx_fsr1.h:986-1199) ----------------------
  * The passes the sample runs either side of EASU/RCAS, as whole-image streaming kernels over rows [y0,y1)

@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+# Several fsr1_shard ranks inside ONE process (tests/test_gpu_sharding.py) use 3 streams each, and their flag-waiting kernels
+# must never share a hardware work queue with the kernel they wait for: ask for more queues than the default 8.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

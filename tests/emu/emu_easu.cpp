@@ -56,7 +56,7 @@ static void run_grid(Kernel kernel, int grid, int threads, const EasuParams& p, 
   }
 }
 
-// variant: the FSR1_EASU_QUAD_VARIANT numbering of launch_easu_h_tiled (2 plain, 6 default, 7, 8, 9, 10).
+// variant: 12 = the production kernel (the number it carried among the round-1 candidates; the others were deleted).
 // Images are RGBA16F, whole frames (row0 = 0).  Returns 0, or -1 for an unknown variant / not exactly 2x.
 extern "C" int emu_easu_h_quad2x(int variant, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
                                  long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
@@ -73,15 +73,8 @@ extern "C" int emu_easu_h_quad2x(int variant, const void* in, int iw, int ih, lo
   const int tiles_y = (m_last - m_first + 1 + CY - 1) / CY, n_tiles = tiles_x * tiles_y;
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   CUtensorMap tmap{(const unsigned char*)in, iw, ih, in_pitch, kQBW, CY + 3, 8};
-  switch (variant) {
-    case 2: run_grid(easu_h_quad2x_kernel<4, 6, 0, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    case 6: run_grid(easu_h_quad2x_kernel<4, 6, 1, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    case 7: run_grid(easu_h_quad2x_kernel<4, 6, 2, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    case 8: run_grid(easu_h_quad2x_kernel<4, 6, 3, false>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    case 9: run_grid(easu_h_quad2x_kernel<4, 6, 3, true>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    case 10: run_grid(easu_h_quad2x_kernel<4, 6, 4, true>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first); break;
-    default: return -1;
-  }
+  if (variant != 12) return -1;  // the production kernel: launch_easu_h_tiled's 2x branch (7 CTAs per SM on the GPU)
+  run_grid(easu_h_quad2x_kernel<4, 7>, grid, NW * 32, p, tmap, tiles_x, n_tiles, m_first);
   return 0;
 }
 
@@ -101,7 +94,7 @@ static int max_footprint(int n_out, int first, int tile, float scale, float offs
 // The any-scale kernel (easu_h_pairs_kernel: vertical pixel pairs, 64x32 tiles).  Returns 0, -1 if unsupported.
 extern "C" int emu_easu_h_pairs(int variant, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
                                 long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
-  if (variant != 0 && variant != 1) return -1;
+  if (variant != 1) return -1;  // the production any-scale kernel
   EasuParams p;
   p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
   p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
@@ -124,8 +117,7 @@ extern "C" int emu_easu_h_pairs(int variant, const void* in, int iw, int ih, lon
         blockIdx = uint3{(unsigned)b, 0, 0};
         gridDim.x = (unsigned)grid;
         blockDim.x = (unsigned)kThreads;
-        if (variant == 1) easu_h_pairs_kernel<1>(p, tmap, BW, BH, tiles_x, n_tiles);
-        else easu_h_pairs_kernel<0>(p, tmap, BW, BH, tiles_x, n_tiles);
+        easu_h_pairs_kernel(p, tmap, BW, BH, tiles_x, n_tiles);
       });
     for (auto& th : ts) th.join();
     pthread_barrier_destroy(&g_cta_barrier);
@@ -133,11 +125,18 @@ extern "C" int emu_easu_h_pairs(int variant, const void* in, int iw, int ih, lon
   return 0;
 }
 
-// The production RCAS kernel (rcas_h_packed_kernel<kClamp, mufu, 4 rows, 4 warps>): grid = 60-pixel spans x 16-row bands.
+// The production RCAS kernel (rcas_h_packed_kernel<kClamp>: 4 rows per lane, 4 warps): grid = 60-pixel spans x 16-row bands.
+// `in` points at logical row in_row0 and holds in_rows rows (a row-slab window; in_row0 = 0, in_rows = h for a whole image).
+extern "C" int emu_rcas_h_packed_win(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
+                                     long long out_pitch, const uint32_t* con, int clamp, int y0, int y1);
 extern "C" int emu_rcas_h_packed(const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
                                  const uint32_t* con, int clamp, int y0, int y1) {
+  return emu_rcas_h_packed_win(in, 0, h, out, w, h, in_pitch, out_pitch, con, clamp, y0, y1);
+}
+extern "C" int emu_rcas_h_packed_win(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
+                                     long long out_pitch, const uint32_t* con, int clamp, int y0, int y1) {
   RcasParams p;
-  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, in_row0, in_rows};
   p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
   memcpy(&p.sharp, &con[0], 4);
   p.sharp_h2 = con[1];
@@ -154,8 +153,8 @@ extern "C" int emu_rcas_h_packed(const void* in, void* out, int w, int h, long l
           blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
           gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
           blockDim.x = (unsigned)threads;
-          if (clamp) rcas_h_packed_kernel<true, false, ROWS, NWARP>(p);
-          else rcas_h_packed_kernel<false, false, ROWS, NWARP>(p);
+          if (clamp) rcas_h_packed_kernel<true>(p);
+          else rcas_h_packed_kernel<false>(p);
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
@@ -215,7 +214,7 @@ extern "C" int emu_rcas_u_packed(int bits, const void* in, void* out, int w, int
   return 0;
 }
 
-// rcas_f32_packed_kernel<kApprox>: RCAS on RGBA32F images (variant 1 = MUFU reciprocal, FSR1_RCAS_F32_VARIANT=1).
+// rcas_f32_packed_kernel: RCAS on RGBA32F images (MUFU reciprocals).
 extern "C" int emu_rcas_f32_packed(int variant, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
                                    const uint32_t* con, int clamp, int y0, int y1) {
   RcasParams p;
@@ -236,7 +235,7 @@ extern "C" int emu_rcas_f32_packed(int variant, const void* in, void* out, int w
           blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
           gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
           blockDim.x = (unsigned)threads;
-          if (variant == 1) rcas_f32_packed_kernel<true>(p); else rcas_f32_packed_kernel<false>(p);
+          rcas_f32_packed_kernel(p);
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < kFWarps; i++) pthread_barrier_destroy(&g_warp_barrier[i]);

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export: " + n
     assert sorted(_lib.SYMBOLS) == names
-    assert L.fsr1_abi_version() == 2
+    assert L.fsr1_abi_version() == 3
 
 
 def test_error_strings_and_validation_without_gpu():
@@ -45,6 +45,14 @@ def test_error_strings_and_validation_without_gpu():
     assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(f32_out), con, 0, 0, 0, None) == -2  # mixed formats
     assert L.fsr1_easu(ctypes.byref(ok_in), ctypes.byref(ok_in), con, 0, 0, 1 << 20, None) == -1  # unknown flag
     assert L.fsr1_rcas(ctypes.byref(ok_in), ctypes.byref(ok_in), con, 0, 0, 1 << 20, None) == -1
+    assert L.fsr1_rcas(ctypes.byref(ok_in), ctypes.byref(ok_in), con, 0, 0, 0, None) == -1      # in place: RCAS reads neighbours it would overwrite
+    # sharding: argument validation happens before any CUDA call
+    h = ctypes.c_void_p()
+    assert L.fsr1_shard_create(ctypes.byref(h), 64, 8, 128, 16, 1, 16, 0, 1, ctypes.c_float(0.25), 0) == -1   # more ranks than rows
+    assert L.fsr1_shard_create(ctypes.byref(h), 64, 64, 128, 128, 1, 4, 4, 1, ctypes.c_float(0.25), 0) == -1  # rank >= world
+    assert L.fsr1_shard_create(ctypes.byref(h), 64, 64, 128, 128, 9, 4, 0, 1, ctypes.c_float(0.25), 0) == -1  # unknown format
+    assert L.fsr1_shard_submit(None, 0, None) == -1 and L.fsr1_shard_status(None) == -1
+    assert b"neighbour" in L.fsr1_error_string(-6)
     small_pitch = _lib.Image(addr, 32, 8, 4, 0, 4, 1, 0)
     assert L.fsr1_easu(ctypes.byref(small_pitch), ctypes.byref(ok_in), con, 0, 0, 0, None) == -1
     # window that does not hold the rows EASU would read -> FSR1_ERR_WINDOW, before any launch
@@ -80,7 +88,7 @@ def test_cpp_filter_mirror_compiles_and_links(tmp_path):
     src.write_text('#include "fidelityfx-fsr_b200/fsr_filter.hpp"\n'
                    'int main(){ fsr1::FSR_Filter f; f.OnCreate(); fsr1::State s; s.renderWidth = 8;\n'
                    '  AU1 c[16]; FsrEasuCon(c, c+4, c+8, c+12, 8.f, 8.f, 8.f, 8.f, 16.f, 16.f);\n'
-                   '  return (fsr1_abi_version() == 2 && c[0] == 0x3f000000u) ? 0 : 1; }\n')
+                   '  return (fsr1_abi_version() == 3 && c[0] == 0x3f000000u) ? 0 : 1; }\n')
     exe = tmp_path / "f"
     libdir = os.path.join(ROOT, "fidelityfx-fsr_b200", "lib")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", ROOT, str(src), "-o", str(exe), "-L", libdir, "-lfsr1_b200",

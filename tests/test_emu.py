@@ -1,11 +1,6 @@
-"""The device code of csrc/fsr1_easu_tiled.cu and csrc/fsr1_rcas_packed.cu compiled for the HOST (tests/emu: one OS thread per CUDA thread, emulated
-TMA / mbarrier / half arithmetic) and checked against the oracle — kernel logic can be debugged without a GPU.
-
-What it proves on CPU, for the 2x EASU kernel family:
-  * the production variant (FSR1_EASU_QUAD_VARIANT=6) stays within the fp16 tolerance of the fp32 oracle — tiling,
-    clamp-to-edge fix-up, persistent tile loop, row ranges and image borders included;
-  * the variants prepared for measurement (7: f32x2-packed per-pixel analysis, 8: integer distance clamp, 9: predicate-free
-    interior path + incremental tile coordinates, 10: 9 with the default's scalar fp32 analysis) produce the SAME BITS as the production variant.
+"""The device code of csrc/fsr1_easu_tiled.cu, csrc/fsr1_rcas_packed.cu and csrc/fsr1_rcas_f32.cu compiled for the HOST (tests/emu: one OS
+thread per CUDA thread, emulated TMA / mbarrier / half arithmetic) and checked against the oracle — kernel logic can be debugged
+without a GPU: tiling, clamp-to-edge fix-up, persistent tile loop, row ranges, image borders, both out-of-image rules.
 The GPU remains the authority on the hardware (tests/test_gpu_parity.py); this is a second, cheaper net."""
 import ctypes
 import os
@@ -17,6 +12,7 @@ import pytest
 import fsr1_b200 as F
 import oracle_lib as ol
 
+PROD = 12   # the production 2x kernel's number in the emulator harness (emu_easu.cpp)
 EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 _lib = None
 
@@ -48,35 +44,23 @@ def test_emulated_production_kernel_within_fp16_tolerance(size, gen):
     ow, oh = 2 * iw, 2 * ih
     src = F.to_half(getattr(F, gen)(iw, ih, 31))
     want = ol.easu(src.astype(np.float32), ow, oh)
-    got = emu_easu(6, src, ow, oh)
+    got = emu_easu(PROD, src, ow, oh)
     assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 5e-3       # GPU tolerance is 1e-2; measured there <= 2.8e-3
     assert (got[..., 3] == np.float16(1.0)).all()
     # one CTA or many, same result (persistent tile loop, double buffering)
-    assert np.array_equal(emu_easu(6, src, ow, oh, ctas=1).view(np.uint16), got.view(np.uint16))
+    assert np.array_equal(emu_easu(PROD, src, ow, oh, ctas=1).view(np.uint16), got.view(np.uint16))
 
 
 def test_emulated_row_range_only_touches_its_rows():
     iw, ih, ow, oh = 64, 36, 128, 72
     src = F.to_half(F.uniform(iw, ih, 5))
-    full = emu_easu(6, src, ow, oh)
-    part = emu_easu(6, src, ow, oh, y0=19, y1=53)
+    full = emu_easu(PROD, src, ow, oh)
+    part = emu_easu(PROD, src, ow, oh, y0=19, y1=53)
     assert np.array_equal(part[19:53].view(np.uint16), full[19:53].view(np.uint16))
     assert not part[:19].view(np.uint16).any() and not part[53:].view(np.uint16).any()
 
 
-@pytest.mark.parametrize("variant", [7, 8, 9, 10])
-def test_prepared_variants_are_bit_identical_to_production(variant):
-    for (iw, ih) in ((64, 36), (70, 23), (33, 17), (99, 40)):   # sizes whose FsrEasuCon scale is exactly 0.5 (97 is not)
-        for gen in (F.uniform, F.structured):
-            src = F.to_half(gen(iw, ih, 77))
-            base = emu_easu(6, src, 2 * iw, 2 * ih)
-            assert np.array_equal(emu_easu(variant, src, 2 * iw, 2 * ih).view(np.uint16), base.view(np.uint16))
-    src = F.to_half(F.uniform(64, 36, 6))
-    assert np.array_equal(emu_easu(variant, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16),
-                          emu_easu(6, src, 128, 72, y0=19, y1=53, ctas=2).view(np.uint16))
-
-
-def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2, variant=0):
+def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2, variant=1):
     ih, iw = src_h.shape[:2]
     y1 = oh if y1 is None else y1
     con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
@@ -91,14 +75,13 @@ def emu_easu_pairs(src_h, ow, oh, y0=0, y1=None, ctas=2, variant=0):
 @pytest.mark.parametrize("shape", [(96, 54, 144, 81), (96, 54, 125, 70), (64, 64, 64, 64), (50, 20, 65, 26), (33, 17, 57, 31),
                                    (64, 36, 128, 72), (96, 54, 192, 81)])
 @pytest.mark.parametrize("gen", ["uniform", "structured"])
-@pytest.mark.parametrize("variant", [0, 1])
-def test_emulated_any_scale_kernel_within_fp16_tolerance(shape, gen, variant):
+def test_emulated_any_scale_kernel_within_fp16_tolerance(shape, gen, variant=1):
     """easu_h_pairs_kernel (1.5x, 1.3x, 1x, ragged sizes, 2x through the generic path, x2.0/y1.5): vertical pixel pairs
     sharing or not sharing an input cell row, box footprints computed per launch, even-aligned box origins."""
     iw, ih, ow, oh = shape
     src = F.to_half(getattr(F, gen)(iw, ih, 31))
     want = ol.easu(src.astype(np.float32), ow, oh)
-    got = emu_easu_pairs(src, ow, oh, variant=variant)       # variant 1 = FSR1_EASU_PAIRS_VARIANT=1 (prepared, not yet timed)
+    got = emu_easu_pairs(src, ow, oh, variant=variant)
     assert np.abs(got.astype(np.float32) - want)[..., :3].max() <= 5e-3
     y0, y1 = oh // 3, 2 * oh // 3 + 1
     part = emu_easu_pairs(src, ow, oh, y0=y0, y1=y1, ctas=1, variant=variant)
@@ -211,9 +194,8 @@ def test_emulated_unorm_rcas_within_one_code(bits, clamp):
                 assert (got[..., 3] == (255 if bits == 8 else 3)).all()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_emulated_fp32_rcas_within_1e5(variant):
-    """rcas_f32_packed_kernel (variant 1 = FSR1_RCAS_F32_VARIANT=1, MUFU reciprocal, prepared): the fp32 fast path is held to
+def test_emulated_fp32_rcas_within_1e5(variant=1):
+    """rcas_f32_packed_kernel (MUFU reciprocals): the fp32 fast path is held to
     1e-5 of the oracle (contraction reorders roundings; bit-exactness is FSR1_FLAG_EXACT's job)."""
     for (w, h) in ((128, 40), (61, 19), (6, 5)):
         for gen in (F.uniform, F.structured):
@@ -229,3 +211,35 @@ def test_emulated_fp32_rcas_within_1e5(variant):
                     want = ol.rcas(src, ol.rcas_con(sharp), clamp)
                     assert np.abs(out - want)[..., :3].max() <= 1e-5
 
+
+
+def test_emulated_rcas_row_window_never_reads_past_the_stored_rows():
+    """A row-slab window whose height is not a multiple of the 4 rows a lane walks (the default 8-GPU split: 270 rows per slab):
+    the last partial chunk requests its rows up front and must not touch memory beyond the rows the window is required to
+    hold (y1 included, y1+1.. not).  The window is placed so that it ENDS at a PROT_NONE guard page: a stray read faults."""
+    import mmap
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    w, h = 128, 40
+    full = F.to_half(F.uniform(w, h, 21))
+    pitch = w * 8
+    page = mmap.PAGESIZE
+    for (y0, y1) in ((0, 6), (8, 18), (3, 13)):
+        need0, need1 = max(y0 - 1, 0), min(y1, h - 1)            # rows RCAS reads (fsr1_rcas's window contract)
+        nbytes = (need1 - need0 + 1) * pitch
+        total = ((nbytes + page - 1) // page + 1) * page
+        buf = mmap.mmap(-1, total)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(buf))
+        assert libc.mprotect(ctypes.c_void_p(base + total - page), page, 0) == 0        # PROT_NONE guard page
+        start = base + total - page - nbytes                                            # window ends exactly at the guard page
+        ctypes.memmove(start, np.ascontiguousarray(full[need0:need1 + 1]).ctypes.data, nbytes)
+        out = np.zeros((h, w, 4), np.uint16)
+        con = (ctypes.c_uint32 * 4)(*ol.rcas_con(0.25))
+        rc = emu_lib().emu_rcas_h_packed_win(ctypes.c_void_p(start), need0, need1 - need0 + 1, ctypes.c_void_p(out.ctypes.data), w, h,
+                                             ctypes.c_longlong(pitch), ctypes.c_longlong(out.strides[0]), con, 0, y0, y1)
+        assert rc == 0
+        want = emu_rcas(full, 0.25)
+        assert np.array_equal(out[y0:y1], want[y0:y1].view(np.uint16))
+        libc.mprotect(ctypes.c_void_p(base + total - page), page, 3)
+        del start
+        buf.close()

@@ -450,3 +450,96 @@ def test_full_size_1080p_to_4k_against_oracle():
     quad = np.stack([pad[fy][:, fx], pad[fy][:, fx + 1], pad[fy + 1][:, fx], pad[fy + 1][:, fx + 1]])
     g = e_got.astype(np.float32)[..., :3]
     assert np.all(g >= quad.min(0)[..., :3]) and np.all(g <= quad.max(0)[..., :3])
+
+
+# ---- BASELINE.json configs at their own size (every pixel against the oracle) ----------------------------------------
+def _full_size_fp16(iw, ih, ow, oh, gen, seed, kernel_prefix):
+    src = F.to_half(getattr(F, gen)(iw, ih, seed))
+    din = dev(src)
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    out = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
+    api.easu(din, tmp, econ)
+    assert api.last_kernel().startswith(kernel_prefix), api.last_kernel()     # the production kernel, not a fallback
+    api.rcas(tmp, out, rcon)
+    assert api.last_kernel().startswith("rcas_h_packed"), api.last_kernel()
+    torch.cuda.synchronize()
+    e_want = ol.easu(src.astype(np.float32), ow, oh)
+    e_got = tmp.cpu().numpy()
+    assert np.abs(e_got.astype(np.float32) - e_want).max() <= TOL16
+    assert np.all(e_got[..., 3] == np.float16(1.0))
+    r_want = ol.rcas(e_got.astype(np.float32), ol.rcas_con(0.25))
+    assert np.abs(out.cpu().numpy().astype(np.float32) - r_want).max() <= TOL16
+    e2e_check(out.cpu().numpy(), ol.rcas(e_want, ol.rcas_con(0.25)), (iw, ih, ow, oh, gen))
+
+
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_full_size_1080p_to_4k_noise_and_structured(gen):
+    """BASELINE configs[1] (the headline), LCG noise and the structured frame."""
+    _full_size_fp16(1920, 1080, 3840, 2160, gen, 12345, "easu_h_quad2x")
+
+
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+@pytest.mark.parametrize("size", [(2560, 1440), (2953, 1661)])
+def test_full_size_configs2_1440p_and_ultra_quality_to_4k(size, gen):
+    """BASELINE configs[2]: 2560x1440 -> 4K (1.5x) and the true Ultra Quality 2953x1661 -> 4K (1.3x, odd width: padded
+    pitch); the any-scale kernel with its per-launch TMA box."""
+    _full_size_fp16(size[0], size[1], 3840, 2160, gen, 12345, "easu_h_vpairs")
+
+
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_full_size_configs3_fp32_1080p_to_4k(gen):
+    """BASELINE configs[3]: RGBA32F at 1080p -> 4K, fast path within 1e-5; and the fp16 path against it (tolerance sweep)."""
+    iw, ih, ow, oh = 1920, 1080, 3840, 2160
+    src = getattr(F, gen)(iw, ih, 12345)
+    din = dev(src)
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros((oh, ow, 4), dtype=torch.float32, device="cuda")
+    for sharp in (0.0, 0.25, 1.0, 2.0):
+        api.upscale(din, tmp, out, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(sharp))
+        torch.cuda.synchronize()
+        if sharp == 0.0:
+            e_want = ol.easu(src, ow, oh)
+            assert np.abs(tmp.cpu().numpy() - e_want).max() <= TOL32
+        r_want = ol.rcas(tmp.cpu().numpy(), ol.rcas_con(sharp))
+        assert np.abs(out.cpu().numpy() - r_want).max() <= TOL32, sharp
+        assert np.abs(out.cpu().numpy() - ol.rcas(e_want, ol.rcas_con(sharp)))[..., :3].max() <= 5e-5, sharp   # end to end (RCAS amplifies)
+
+
+def test_full_size_configs4_2160p_to_8k_in_8_slabs():
+    """BASELINE configs[4]: 3840x2160 -> 7680x4320 RGBA16F cut into 8 row slabs of 540 rows (2 halo rows each side,
+    61 440 B per message) through the sharded data plane (8 ranks on this one device, halo by direct stores), bit-identical
+    to the single-GPU frame, and that against the oracle on bands that straddle every slab boundary."""
+    iw, ih, ow, oh, world = 3840, 2160, 7680, 4320, 8
+    src = F.to_half(F.structured(iw, ih, 4242))
+    frame = torch.from_numpy(src).cuda()
+    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, slots=1, halo="p2p") for r in range(world)]
+    for r, u in enumerate(ups):
+        u.attach_local(ups[r - 1] if r > 0 else None, ups[r + 1] if r + 1 < world else None)
+        assert u.plan.halo_bytes(r, iw, 8) == (2 if 0 < r < world - 1 else 1) * 61440
+    s = torch.cuda.current_stream()
+    for r, u in enumerate(ups):
+        o0, o1 = u.plan.owned_in_rows(r)
+        u.input(0).copy_(frame[o0:o1])
+    for u in ups:
+        u.submit(0, s)
+    for u in ups:
+        u.wait(0, s)
+    sharded = torch.cat([u.output(0) for u in ups])
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    whole = torch.zeros_like(tmp)
+    api.upscale(frame, tmp, whole, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25))
+    torch.cuda.synchronize()
+    for u in ups:
+        u.status()
+    assert torch.equal(sharded, whole)
+    got = whole.cpu().numpy().astype(np.float32)
+    f32 = src.astype(np.float32)
+    for r in range(1, world):
+        yb = r * oh // world
+        y0, y1 = yb - 24, yb + 24
+        e = ol.easu(f32, ow, oh, y0=y0 - 1, y1=y1 + 1)
+        want = ol.rcas(e, ol.rcas_con(0.25), y0=y0, y1=y1)
+        assert np.abs(got[y0:y1] - want[y0:y1])[..., :3].max() <= TOL16, r
+    for u in ups:
+        u.close()

@@ -1,6 +1,7 @@
-"""Row-slab sharding: plan geometry, and the halo exchange on 2 ranks over gloo (CPU).  The per-slab compute
-in these CPU tests is the oracle standing in for the kernels (test infrastructure); the GPU twin is in
-test_gpu_parity.py::test_slabs_compose and bench.py --gpus N."""
+"""Row-slab sharding: plan geometry, and the halo exchange on 2-3 ranks over gloo (CPU) — both the free functions and
+ShardedUpscaler's own exchange code (halo="nccl": the code bench.py times when asked for the NCCL data plane).  The per-slab
+compute in these CPU tests is the oracle standing in for the kernels (test infrastructure); the GPU twins are
+tests/test_gpu_sharding.py (direct NVLink/IPC data plane, 1 GPU and N GPUs) and bench.py --gpus N (parity printed per run)."""
 import os
 import sys
 
@@ -15,7 +16,7 @@ import oracle_lib as ol
 
 
 @pytest.mark.parametrize("in_h,out_h,world", [(1080, 2160, 8), (2160, 4320, 8), (1440, 2160, 4), (1661, 2160, 3),
-                                               (17, 31, 2), (9, 9, 4), (5, 40, 8)])
+                                               (17, 31, 2), (9, 9, 4), (16, 40, 8)])
 def test_plan_geometry(in_h, out_h, world):
     econ = ol.easu_con(64, in_h, 128, out_h)
     plan = F.SlabPlan(in_h, out_h, world, econ)
@@ -106,3 +107,51 @@ def test_batched_halo_exchange_of_several_frames_gloo(shape, world):
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker_many, args=(world, port, shape, 3), nprocs=world, join=True)
 
+
+
+def _worker_upscaler(rank, world, port, shape, tmpdir):
+    """ShardedUpscaler(halo="nccl") on CPU tensors over gloo: its _exchange / exchange_many are what move the rows."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    iw, ih, ow, oh = shape
+    nslots = 3
+    frames = [F.uniform(iw, ih, 500 + t) for t in range(nslots)]
+    up = F.ShardedUpscaler(iw, ih, ow, oh, world, rank, dtype=torch.float32, device="cpu", halo="nccl", slots=nslots)
+    plan = up.plan
+    o0, o1 = plan.owned_in_rows(rank)
+    w0, w1 = plan.window_rows(rank)
+    n0, n1 = plan.needed_in_rows(rank)
+    for s in range(nslots):
+        up.windows[s].fill_(float("nan"))
+        up.input(s).copy_(torch.from_numpy(frames[s][o0:o1].copy()))
+    nops = up._exchange(0)                       # one frame
+    sends, recvs = plan.transfers(rank)
+    assert nops == len(sends) + len(recvs)
+    assert up.exchange_many([1, 2]) == 2 * nops  # two frames in one group
+    for s in range(nslots):
+        got = up.windows[s].numpy()[n0 - w0:n1 - w0]
+        assert np.array_equal(got, frames[s][n0:n1]), "slot %d: halo rows did not land in the right window rows" % s
+    # slab compute (oracle stand-in for the kernels) from the upscaler's own window, slot 2
+    padded = np.zeros_like(frames[2])
+    padded[w0:w1] = up.windows[2].numpy()
+    e0, e1 = plan.easu_rows(rank)
+    y0, y1 = plan.out_rows(rank)
+    out = ol.rcas(ol.easu(padded, ow, oh, up.econ, y0=e0, y1=e1), up.rcon, False, y0=y0, y1=y1)
+    np.save(os.path.join(tmpdir, "u%d.npy" % rank), out[y0:y1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,world", [((48, 40, 96, 80), 2), ((40, 33, 52, 43), 3)])
+def test_sharded_upscaler_exchange_gloo(shape, world, tmp_path):
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_upscaler, args=(world, port, shape, str(tmp_path)), nprocs=world, join=True)
+    iw, ih, ow, oh = shape
+    want = ol.rcas(ol.easu(F.uniform(iw, ih, 502), ow, oh), ol.rcas_con(0.25), False)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "u%d.npy" % r)) for r in range(world)])
+    assert np.array_equal(got, want)
+
+
+def test_plan_rejects_empty_slabs():
+    with pytest.raises(ValueError):
+        F.SlabPlan(5, 40, 8, ol.easu_con(64, 5, 128, 40))

@@ -1,6 +1,5 @@
 """Times EASU and RCAS on R8G8B8A8_UNORM images at 1080p -> 4K (the formats the sample renders into).
-   python tools/unorm_time.py                      direct kernels (default)
-   FSR1_UNORM_TILED=1 python tools/unorm_time.py    TMA-tiled EASU + packed RCAS (prepared at the end of round 1)"""
+   python tools/unorm_time.py"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 """Times EASU and RCAS separately (CUDA events, ring of frames > L2) and reports per-stage max error.
-Usage: FSR1_EASU_QUAD_VARIANT=.. FSR1_RCAS_VARIANT=.. python tools/variant_time.py [2x|1.5x|1.3x]"""
+Usage: python tools/variant_time.py [2x|1.5x|1.3x]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
