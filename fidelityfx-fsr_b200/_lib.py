@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfsr1_b200.so")
 FSR1_OK = 0
 FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_RGB10A2_UNORM = 1, 2, 3, 4
 FLAG_RCAS_CLAMP, FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_H_REFERENCE, FLAG_PRECISE = 1, 2, 4, 8, 16, 32
-FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE = 64, 128, 256
+FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE, FLAG_FUSED = 64, 128, 256, 512
 SHARD_ONE_STREAM, SHARD_SKIP_HALO, SHARD_HANDLE_BYTES = 1 << 16, 1 << 17, 64
 
 # every symbol include/fsr1_b200.h declares

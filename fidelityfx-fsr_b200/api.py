@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import FORMAT_RGB10A2_UNORM, FORMAT_RGBA8_UNORM  # noqa: F401
-from ._lib import FLAG_OUTPUT_SQUARE  # noqa: F401
+from ._lib import FLAG_FUSED, FLAG_OUTPUT_SQUARE  # noqa: F401
 from ._lib import (FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_H_REFERENCE, FLAG_NO_RCAS, FLAG_PRECISE, FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_RCAS_CLAMP, FORMAT_RGBA16F,  # noqa: F401
                    FORMAT_RGBA32F, Fsr1Error, Image)
 

@@ -65,7 +65,7 @@ float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 // every flag include/fsr1_b200.h defines
 constexpr uint32_t kAllFlags = FSR1_FLAG_RCAS_CLAMP | FSR1_FLAG_EXACT | FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_NO_RCAS |
                                FSR1_FLAG_H_REFERENCE | FSR1_FLAG_PRECISE | FSR1_FLAG_RCAS_DENOISE |
-                               FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE;
+                               FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE | FSR1_FLAG_FUSED;
 
 bool window_holds(const fsr1_image* im, int first, int last) {  // logical rows [first,last]
   return first >= (int)im->row0 && last < (int)(im->row0 + im->rows);
@@ -221,25 +221,31 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   const bool exact = (flags & FSR1_FLAG_EXACT) != 0;
   cudaError_t e = cudaErrorNotSupported;
   const char* name = "";
+  bool squared = false;  // the Sample.x hook folded into the kernel's store (c *= c before the one rounding)
+  const int fused_square = (flags & FSR1_FLAG_OUTPUT_SQUARE) ? 4 : 0;
   if (flags & FSR1_FLAG_H_REFERENCE) {
     if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
     e = launch_rcas_href(p, s, &name);
-  } else if (p.options) {
-    // the reference's optional RCAS variants run on the direct kernels (fp32 arithmetic); the packed kernels
-    // implement the configuration the sample ships (neither macro defined)
   } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    p.options |= fused_square;  // the reference's options are template bits of the packed kernels: no slower fallback
     e = launch_rcas_h_packed(p, s, &name);
+    squared = e == cudaSuccess;
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
+    p.options |= fused_square;
     e = launch_rcas_f32_packed(p, s, &name);
+    squared = e == cudaSuccess;
   } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
              !(flags & (FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_PRECISE))) {
+    p.options |= fused_square;
     e = launch_rcas_u_packed(p, (int)in->format, s, &name);
+    squared = e == cudaSuccess;
   }
+  if (e == cudaErrorNotSupported) p.options &= 3;
   if (e == cudaErrorNotSupported) e = launch_rcas_direct(p, (int)in->format, exact, s, &name);
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;
   g_launches.fetch_add(1);
-  if (flags & FSR1_FLAG_OUTPUT_SQUARE) return square_rows(out, y0, y1, s);
+  if ((flags & FSR1_FLAG_OUTPUT_SQUARE) && !squared) return square_rows(out, y0, y1, s);  // direct / H-reference kernels: separate pass
   return FSR1_OK;
 }
 
@@ -248,9 +254,35 @@ int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* 
   if (!out) return FSR1_ERR_INVALID_ARGUMENT;
   if (y1 == 0) y1 = out->height;
   if (flags & FSR1_FLAG_NO_RCAS) return fsr1_easu(in, out, easu_con, y0, y1, flags, stream);
-  if (!tmp) return FSR1_ERR_INVALID_ARGUMENT;
   // EASU also produces the one-row apron RCAS reads, so a row slab needs no second exchange
   const uint32_t e0 = y0 == 0 ? 0 : y0 - 1, e1 = y1 >= out->height ? out->height : y1 + 1;
+  if ((flags & FSR1_FLAG_FUSED) && in && easu_con && rcas_con && in->format == FSR1_FORMAT_RGBA16F && out->format == FSR1_FORMAT_RGBA16F &&
+      !(flags & (FSR1_FLAG_EXACT | FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_H_REFERENCE | FSR1_FLAG_PRECISE | FSR1_FLAG_RCAS_CLAMP |
+                 FSR1_FLAG_RCAS_DENOISE | FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE))) {
+    int rc;
+    if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
+    if (flags & ~kAllFlags) return FSR1_ERR_INVALID_ARGUMENT;
+    if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
+    if (!window_holds(out, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
+    uint32_t r0, r1;
+    fsr1_easu_input_rows(easu_con, in->height, e0, e1, &r0, &r1);
+    if (!window_holds(in, (int)r0, (int)r1)) return FSR1_ERR_WINDOW;
+    EasuParams p;
+    p.in = view_of(in);
+    p.out = view_of(out);
+    p.c0x = as_float(easu_con[0]); p.c0y = as_float(easu_con[1]); p.c0z = as_float(easu_con[2]); p.c0w = as_float(easu_con[3]);
+    p.y0 = (int)y0; p.y1 = (int)y1;
+    const char* name = "";
+    const cudaError_t e = launch_fused_h(p, rcas_con[1], 0, static_cast<cudaStream_t>(stream), &name);
+    if (e == cudaSuccess) {
+      t_last_kernel = name;
+      g_launches.fetch_add(1);
+      return FSR1_OK;
+    }
+    if (e != cudaErrorNotSupported) return cuda_fail(e);
+  }
+  flags &= ~(uint32_t)FSR1_FLAG_FUSED;
+  if (!tmp) return FSR1_ERR_INVALID_ARGUMENT;
   int rc = fsr1_easu(in, tmp, easu_con, e0, e1, flags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, stream);  // last pass only
   if (rc != FSR1_OK) return rc;
   return fsr1_rcas(tmp, out, rcas_con, y0, y1, flags, stream);

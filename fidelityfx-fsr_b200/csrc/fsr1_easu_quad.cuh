@@ -175,20 +175,20 @@ template <typename ST> struct GlobalSink {
   }
 };
 
-// The quad of cell (lane, r) of a tile: taps from `tile` (row pitch kQBW texels), per-texel terms from S (row pitch kQSW).
+// The quad of cell (lane, r) of a tile: taps from `tile` (row pitch kPitch texels), per-texel terms from S (row pitch kSPitch).
 // doTop / doBottom select the output rows 2m+1 / 2m+2; the sink receives each row's pixel pair.
-template <typename Sink>
+template <typename Sink, int kPitch = kQBW, int kSPitch = kQSW>
 __device__ __forceinline__ void quad_compute(const uint2* __restrict__ tile, const float4* __restrict__ S, int lane, int r,
                                              bool doTop, bool doBottom, const Sink& sink) {
   uint2 tp[4][4];
-  const uint2* t0 = tile + r * kQBW + lane;
+  const uint2* t0 = tile + r * kPitch + lane;
 #pragma unroll
   for (int R = 0; R < 4; R++)
 #pragma unroll
     for (int K = 0; K < 4; K++)
-      if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kQBW + K];
-  const float4* s0 = S + r * kQSW + lane;
-  const float4 f = s0[0], g = s0[1], j = s0[kQSW], k = s0[kQSW + 1];
+      if (!((R == 0 || R == 3) && (K == 0 || K == 3))) tp[R][K] = t0[R * kPitch + K];
+  const float4* s0 = S + r * kSPitch + lane;
+  const float4 f = s0[0], g = s0[1], j = s0[kSPitch], k = s0[kSPitch + 1];
   // de-ringing bounds of the quad: min/max of f,g,j,k per channel, broadcast to both lanes
   const __half2 mnRG = __hmin2(__hmin2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmin2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));
   const __half2 mxRG = __hmax2(__hmax2(u2h2(tp[1][1].x), u2h2(tp[1][2].x)), __hmax2(u2h2(tp[2][1].x), u2h2(tp[2][2].x)));

@@ -22,7 +22,7 @@
 //                         pixels sharing one 4x4 window (fsr1_easu_quad.cuh).  Persistent CTAs, TMA double-buffered:
 //                         tile i+1 loads while tile i computes; tiles strictly inside the image take a predicate-free
 //                         copy of the per-quad body; tile coordinates advance incrementally.  7 CTAs x 4 warps per SM.
-//   easu_u_quad2x_kernel  the same for R8G8B8A8 / R10G10B10A2 images (4-byte texels, decode pass, fused re-encode).
+//   easu_u_quad2x_kernel  the same for R8G8B8A8_UNORM images (4-byte texels, decode pass, fused re-encode).
 //   easu_h_pairs_kernel   any other scale >= 1; 64x32 output tile per CTA; lane = one output column and a VERTICAL
 //                         pixel pair.
 #include "fsr1_easu_quad.cuh"
@@ -458,22 +458,17 @@ static QuadGrid quad_grid(const EasuParams& p, int cy, int ctas_per_sm) {
   return g;
 }
 
-// UNORM images at exactly 2x (the caller routes FSR1_FLAG_PRECISE / _EXACT requests to the fp32 direct kernels instead:
-// half arithmetic is coarser than the codes of R10G10B10A2)
+// R8G8B8A8_UNORM images at exactly 2x.  (R10G10B10A2 stays on the fp32 direct kernel: half taps are coarser than its codes,
+// 2-4 code values off where the 8-bit format is within one; the caller also routes FSR1_FLAG_PRECISE / _EXACT there.)
 cudaError_t launch_easu_u_tiled(const EasuParams& p, int format, cudaStream_t s, const char** name) {
-  if (format != 3 && format != 4) return cudaErrorNotSupported;
+  if (format != 3) return cudaErrorNotSupported;
   if ((reinterpret_cast<uintptr_t>(p.in.base) & 15) || (p.in.pitch & 15) || !is_2x(p)) return cudaErrorNotSupported;  // TMA
   constexpr int NW = 4, CY = 2 * NW;
   CUtensorMap tmap;
   if (!make_tmap(&tmap, p.in, kUBW, CY + 3, CU_TENSOR_MAP_DATA_TYPE_UINT32)) return cudaErrorNotSupported;
   const QuadGrid g = quad_grid(p, CY, 6);
-  if (format == 3) {
-    easu_u_quad2x_kernel<NW, 6, 8><<<g.grid, NW * 32, 0, s>>>(p, tmap, g.tiles_x, g.n_tiles, g.m_first);
-    *name = "easu_u8_quad2x<4w,6/sm,tma2>";
-  } else {
-    easu_u_quad2x_kernel<NW, 6, 10><<<g.grid, NW * 32, 0, s>>>(p, tmap, g.tiles_x, g.n_tiles, g.m_first);
-    *name = "easu_u10_quad2x<4w,6/sm,tma2>";
-  }
+  easu_u_quad2x_kernel<NW, 6, 8><<<g.grid, NW * 32, 0, s>>>(p, tmap, g.tiles_x, g.n_tiles, g.m_first);
+  *name = "easu_u8_quad2x<4w,6/sm,tma2>";
   return cudaGetLastError();
 }
 

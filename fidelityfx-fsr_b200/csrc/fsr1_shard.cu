@@ -402,11 +402,28 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   fsr1_image tmp = make_img(s->tmp + (uint64_t)slot * s->tmp_slot_stride, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a,
                             s->easu_rows.b - s->easu_rows.a, s->format);
   const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+  uint32_t* cu = up ? reinterpret_cast<uint32_t*>(s->peer[kFromUp]) + credit_idx(slot, kFromDown) : nullptr;
+  uint32_t* cd = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
+  if (kflags & FSR1_FLAG_FUSED) {
+    // one kernel per frame where the fused EASU->RCAS kernel applies (fsr1_upscale falls back to the two kernels otherwise);
+    // consecutive frames overlap on the two streams alternately
+    cudaStream_t sf = one_stream ? se : ((q + slot) & 1 ? sr : se);
+    if (sf != se) {  // order the frame's stream after the halo wait / input event recorded on se
+      if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
+      if ((e = cudaStreamWaitEvent(sf, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
+    }
+    int rc = fsr1_upscale(&win, &tmp, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, sf);
+    if (rc != FSR1_OK) return rc;
+    if (up || down) {
+      credit_signal_kernel<<<1, 32, 0, sf>>>(cu, cd, q);
+      if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if ((e = cudaEventRecord(s->ev_rcas[slot], sf)) != cudaSuccess) return cuda_rc(e);
+    return FSR1_OK;
+  }
   int rc = fsr1_easu(&win, &tmp, s->econ, s->easu_rows.a, s->easu_rows.b, kflags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, se);
   if (rc != FSR1_OK) return rc;
   if (up || down) {
-    uint32_t* cu = up ? reinterpret_cast<uint32_t*>(s->peer[kFromUp]) + credit_idx(slot, kFromDown) : nullptr;
-    uint32_t* cd = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
     credit_signal_kernel<<<1, 32, 0, se>>>(cu, cd, q);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
   }

@@ -28,6 +28,7 @@ unsigned char* fsr1_emu_dynamic_smem() { return g_dynamic_smem; }
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_easu_tiled.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_packed.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_f32.cu"
+#include "../../fidelityfx-fsr_b200/csrc/fsr1_fused.cu"
 
 using namespace fsr1;
 
@@ -127,14 +128,31 @@ extern "C" int emu_easu_h_pairs(int variant, const void* in, int iw, int ih, lon
 
 // The production RCAS kernel (rcas_h_packed_kernel<kClamp>: 4 rows per lane, 4 warps): grid = 60-pixel spans x 16-row bands.
 // `in` points at logical row in_row0 and holds in_rows rows (a row-slab window; in_row0 = 0, in_rows = h for a whole image).
-extern "C" int emu_rcas_h_packed_win(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
-                                     long long out_pitch, const uint32_t* con, int clamp, int y0, int y1);
+// opts: bit 0 FSR_RCAS_DENOISE, bit 1 FSR_RCAS_PASSTHROUGH_ALPHA, bit 2 the Sample.x output square (kRcas* of fsr1_rcas_math.cuh)
+extern "C" int emu_rcas_h_packed_opt(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
+                                     long long out_pitch, const uint32_t* con, int clamp, int y0, int y1, int opts);
 extern "C" int emu_rcas_h_packed(const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
                                  const uint32_t* con, int clamp, int y0, int y1) {
-  return emu_rcas_h_packed_win(in, 0, h, out, w, h, in_pitch, out_pitch, con, clamp, y0, y1);
+  return emu_rcas_h_packed_opt(in, 0, h, out, w, h, in_pitch, out_pitch, con, clamp, y0, y1, 0);
 }
 extern "C" int emu_rcas_h_packed_win(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
                                      long long out_pitch, const uint32_t* con, int clamp, int y0, int y1) {
+  return emu_rcas_h_packed_opt(in, in_row0, in_rows, out, w, h, in_pitch, out_pitch, con, clamp, y0, y1, 0);
+}
+template <typename FM, bool kClamp> static void emu_rcas_dispatch(const RcasParams& p, int opts) {
+  switch (opts & 7) {
+    case 0: rcas_packed_kernel<FM, kClamp, 0>(p); break;
+    case 1: rcas_packed_kernel<FM, kClamp, 1>(p); break;
+    case 2: rcas_packed_kernel<FM, kClamp, 2>(p); break;
+    case 3: rcas_packed_kernel<FM, kClamp, 3>(p); break;
+    case 4: rcas_packed_kernel<FM, kClamp, 4>(p); break;
+    case 5: rcas_packed_kernel<FM, kClamp, 5>(p); break;
+    case 6: rcas_packed_kernel<FM, kClamp, 6>(p); break;
+    default: rcas_packed_kernel<FM, kClamp, 7>(p); break;
+  }
+}
+extern "C" int emu_rcas_h_packed_opt(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch,
+                                     long long out_pitch, const uint32_t* con, int clamp, int y0, int y1, int opts) {
   RcasParams p;
   p.in = ImgView{(unsigned char*)in, in_pitch, w, h, in_row0, in_rows};
   p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
@@ -153,8 +171,8 @@ extern "C" int emu_rcas_h_packed_win(const void* in, int in_row0, int in_rows, v
           blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
           gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
           blockDim.x = (unsigned)threads;
-          if (clamp) rcas_h_packed_kernel<true>(p);
-          else rcas_h_packed_kernel<false>(p);
+          if (clamp) emu_rcas_dispatch<FmtHalf, true>(p, opts);
+          else emu_rcas_dispatch<FmtHalf, false>(p, opts);
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
@@ -184,8 +202,14 @@ extern "C" int emu_easu_u_quad2x(int bits, const void* in, int iw, int ih, long 
 }
 
 // rcas_u_packed_kernel: RCAS on UNORM images (bits = 8 or 10), 4 bytes per texel.
+extern "C" int emu_rcas_u_packed_opt(int bits, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                                     const uint32_t* con, int clamp, int y0, int y1, int opts);
 extern "C" int emu_rcas_u_packed(int bits, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
                                  const uint32_t* con, int clamp, int y0, int y1) {
+  return emu_rcas_u_packed_opt(bits, in, out, w, h, in_pitch, out_pitch, con, clamp, y0, y1, 0);
+}
+extern "C" int emu_rcas_u_packed_opt(int bits, const void* in, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                                     const uint32_t* con, int clamp, int y0, int y1, int opts) {
   if (bits != 8 && bits != 10) return -1;
   RcasParams p;
   p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
@@ -205,8 +229,8 @@ extern "C" int emu_rcas_u_packed(int bits, const void* in, void* out, int w, int
           blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
           gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
           blockDim.x = (unsigned)threads;
-          if (bits == 8) { if (clamp) rcas_u_packed_kernel<true, 8>(p); else rcas_u_packed_kernel<false, 8>(p); }
-          else { if (clamp) rcas_u_packed_kernel<true, 10>(p); else rcas_u_packed_kernel<false, 10>(p); }
+          if (bits == 8) { if (clamp) emu_rcas_dispatch<FmtUnorm<8>, true>(p, opts); else emu_rcas_dispatch<FmtUnorm<8>, false>(p, opts); }
+          else { if (clamp) emu_rcas_dispatch<FmtUnorm<10>, true>(p, opts); else emu_rcas_dispatch<FmtUnorm<10>, false>(p, opts); }
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < NWARP; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
@@ -235,7 +259,7 @@ extern "C" int emu_rcas_f32_packed(int variant, const void* in, void* out, int w
           blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
           gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
           blockDim.x = (unsigned)threads;
-          rcas_f32_packed_kernel(p);
+          rcas_f32_packed_kernel<0>(p);
         });
       for (auto& th : ts) th.join();
       for (int i = 0; i < kFWarps; i++) pthread_barrier_destroy(&g_warp_barrier[i]);
@@ -243,3 +267,32 @@ extern "C" int emu_rcas_f32_packed(int variant, const void* in, void* out, int w
   return 0;
 }
 
+
+// fused_h_quad2x_kernel: EASU -> RCAS in one kernel (RGBA16F, 2x), launch geometry of launch_fused_h with `ctas` CTAs.
+extern "C" int emu_fused_h(const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh, long long out_pitch,
+                           const uint32_t* rcon, int y0, int y1, int ctas) {
+  constexpr int NW = 4;
+  using C = FusedCfg<NW>;
+  FusedParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
+  p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
+  p.y0 = y0; p.y1 = y1; p.sharp_h2 = rcon[1];
+  p.n_strips = ((ow + 1) / 2 + kStripCells - 1) / kStripCells;
+  CUtensorMap tmap{(const unsigned char*)in, iw, ih, in_pitch, kFBW, C::kBH, 8};
+  const int threads = NW * 32;
+  for (int b = 0; b < ctas; b++) {
+    pthread_barrier_init(&g_cta_barrier, nullptr, (unsigned)threads);
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; t++)
+      ts.emplace_back([=, &p, &tmap]() {
+        threadIdx = uint3{(unsigned)t, 0, 0};
+        blockIdx = uint3{(unsigned)b, 0, 0};
+        gridDim.x = (unsigned)ctas;
+        blockDim.x = (unsigned)threads;
+        fused_h_quad2x_kernel<NW, 6>(p, tmap);
+      });
+    for (auto& th : ts) th.join();
+    pthread_barrier_destroy(&g_cta_barrier);
+  }
+  return 0;
+}

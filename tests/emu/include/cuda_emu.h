@@ -88,6 +88,7 @@ inline __half2 __hadd2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) 
 inline __half2 __hsub2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) - h2f(b.x)), d2h((double)h2f(a.y) - h2f(b.y))); }
 inline __half2 __hmul2_sat(__half2 a, __half2 b) { return mkh2(f2h(__saturatef((float)((double)h2f(a.x) * h2f(b.x)))), f2h(__saturatef((float)((double)h2f(a.y) * h2f(b.y))))); }
 inline __half2 __hneg2(__half2 a) { a.x.b ^= 0x8000; a.y.b ^= 0x8000; return a; }
+inline __half2 __habs2(__half2 a) { a.x.b &= 0x7fff; a.y.b &= 0x7fff; return a; }
 inline __half hmin1(__half a, __half b) { return f2h(fminf(h2f(a), h2f(b))); }  // non-propagating, like HMNMX2
 inline __half hmax1(__half a, __half b) { return f2h(fmaxf(h2f(a), h2f(b))); }
 inline __half2 __hmin2(__half2 a, __half2 b) { return mkh2(hmin1(a.x, b.x), hmin1(a.y, b.y)); }

@@ -243,3 +243,69 @@ def test_emulated_rcas_row_window_never_reads_past_the_stored_rows():
         libc.mprotect(ctypes.c_void_p(base + total - page), page, 3)
         del start
         buf.close()
+
+
+@pytest.mark.parametrize("opts", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_rcas_options_on_the_packed_kernel(opts):
+    """FSR_RCAS_DENOISE (bit 0), FSR_RCAS_PASSTHROUGH_ALPHA (bit 1) and the Sample.x output square (bit 2) are template bits of
+    the production packed kernel (no fallback to the direct kernel, no extra pass): against the oracle built with the same
+    options, RGBA16F and R8G8B8A8."""
+    denoise, alpha, square = bool(opts & 1), bool(opts & 2), bool(opts & 4)
+    w, h = 128, 40
+    for gen in (F.uniform, F.structured):
+        src = F.to_half(gen(w, h, 17))
+        con = (ctypes.c_uint32 * 4)(*ol.rcas_con(0.25))
+        for clamp in (False, True):
+            want = ol.rcas(src.astype(np.float32), ol.rcas_con(0.25), clamp, denoise=denoise, alpha=alpha)
+            if square:
+                want[..., :3] = want[..., :3] * want[..., :3]
+            s16 = np.ascontiguousarray(src.view(np.uint16))
+            out = np.zeros((h, w, 4), np.uint16)
+            rc = emu_lib().emu_rcas_h_packed_opt(ctypes.c_void_p(s16.ctypes.data), 0, h, ctypes.c_void_p(out.ctypes.data), w, h,
+                                                 ctypes.c_longlong(s16.strides[0]), ctypes.c_longlong(out.strides[0]), con,
+                                                 1 if clamp else 0, 0, h, opts)
+            assert rc == 0
+            got = out.view(np.float16).astype(np.float32)
+            assert np.abs(got - want)[..., :3].max() <= 4e-3, (gen.__name__, clamp)
+            if alpha:
+                assert np.array_equal(out[..., 3], s16[..., 3])          # the centre pixel's alpha, bit for bit
+            else:
+                assert (out.view(np.float16)[..., 3] == np.float16(1.0)).all()
+        # R8G8B8A8
+        raw = _quantise(gen(w, h, 18), 8)
+        raw[..., 3] = np.random.default_rng(3).integers(0, 256, size=(h, w))
+        fin = (raw.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+        want = ol.rcas(fin, ol.rcas_con(0.25), False, denoise=denoise, alpha=alpha)
+        if square:
+            want[..., :3] = want[..., :3] * want[..., :3]
+        wq = _quantise(want[..., :3], 8)
+        src8 = np.ascontiguousarray(_pack_unorm(raw, 8))
+        out8 = np.zeros_like(src8)
+        rc = emu_lib().emu_rcas_u_packed_opt(8, ctypes.c_void_p(src8.ctypes.data), ctypes.c_void_p(out8.ctypes.data), w, h,
+                                             ctypes.c_longlong(src8.strides[0]), ctypes.c_longlong(out8.strides[0]), con, 0, 0, h, opts)
+        assert rc == 0
+        got8 = _unpack_unorm(out8, 8)
+        assert np.abs(got8[..., :3].astype(np.int64) - wq.astype(np.int64)).max() <= 1
+        assert np.array_equal(got8[..., 3], raw[..., 3] if alpha else np.full((h, w), 255))
+
+
+@pytest.mark.parametrize("size", [(64, 36), (70, 23), (33, 17), (99, 40), (5, 3)])
+@pytest.mark.parametrize("ctas", [1, 3, 7])
+def test_emulated_fused_kernel_is_bit_identical_to_the_two_kernel_path(size, ctas):
+    """fused_h_quad2x_kernel (EASU -> shared-memory intermediate -> RCAS, column strips, rolling rows): the same bits as
+    easu_h_quad2x_kernel followed by rcas_packed_kernel through an fp16 intermediate, for any number of CTAs (run boundaries
+    fall anywhere), several strips (width > 62), image borders (out-of-image taps read 0), and row ranges (slabs)."""
+    iw, ih = size
+    ow, oh = 2 * iw, 2 * ih
+    for gen in (F.uniform, F.structured):
+        src = F.to_half(gen(iw, ih, 55))
+        want = emu_rcas(emu_easu(PROD, src, ow, oh), 0.25)
+        con = (ctypes.c_uint32 * 4)(*ol.rcas_con(0.25))
+        s16 = np.ascontiguousarray(src.view(np.uint16))
+        for (y0, y1) in ((0, oh), (oh // 3, 2 * oh // 3 + 1)):
+            out = np.zeros((oh, ow, 4), np.uint16)
+            rc = emu_lib().emu_fused_h(ctypes.c_void_p(s16.ctypes.data), iw, ih, ctypes.c_longlong(s16.strides[0]),
+                                       ctypes.c_void_p(out.ctypes.data), ow, oh, ctypes.c_longlong(out.strides[0]), con, y0, y1, ctas)
+            assert rc == 0
+            assert np.array_equal(out[y0:y1], want.view(np.uint16)[y0:y1]), (gen.__name__, y0, y1)
+            assert not out[:y0].any() and not out[y1:].any()

@@ -543,3 +543,122 @@ def test_full_size_configs4_2160p_to_8k_in_8_slabs():
         assert np.abs(got[y0:y1] - want[y0:y1])[..., :3].max() <= TOL16, r
     for u in ups:
         u.close()
+
+
+@pytest.mark.parametrize("opts", [1, 2, 3, 4, 5, 6, 7])
+def test_rcas_options_run_on_the_packed_kernels(opts):
+    """FSR_RCAS_DENOISE / FSR_RCAS_PASSTHROUGH_ALPHA / the Sample.x square are template bits of the production kernels
+    (RGBA16F, RGBA32F, R8G8B8A8): same kernel family as the plain configuration, no extra pass, results against the oracle
+    built with the same options (ffx_fsr1.h:688-702,731-739,761-763; FSR_Pass.hlsl:93-94)."""
+    denoise, alpha, square = bool(opts & 1), bool(opts & 2), bool(opts & 4)
+    fl = (api.FLAG_RCAS_DENOISE if denoise else 0) | (api.FLAG_RCAS_PASSTHROUGH_ALPHA if alpha else 0) | (api.FLAG_OUTPUT_SQUARE if square else 0)
+    w, h = 259, 141
+    for gen in ("uniform", "structured"):
+        img = getattr(F, gen)(w, h, 36)
+        for clamp in (0, api.FLAG_RCAS_CLAMP):
+            rc = ol.rcas_con(0.25)
+            def want_of(x):
+                r = ol.rcas(x, rc, bool(clamp), denoise=denoise, alpha=alpha)
+                if square:
+                    r[..., :3] = r[..., :3] * r[..., :3]
+                return r
+            n0 = api.launch_count()
+            got = gpu_rcas(img, 0.25, fl | clamp)
+            assert api.last_kernel().startswith("rcas_f32_packed") and api.launch_count() == n0 + 1
+            assert np.abs(got - want_of(img))[..., :3].max() <= (TOL32 if not square else 2e-5)
+            assert np.array_equal(got[..., 3], img[..., 3] if alpha else np.ones((h, w), np.float32))
+            imh = F.to_half(img)
+            n0 = api.launch_count()
+            goth = gpu_rcas(imh, 0.25, fl | clamp)
+            assert api.last_kernel().startswith("rcas_h_packed") and api.launch_count() == n0 + 1
+            assert np.abs(goth.astype(np.float32) - want_of(imh.astype(np.float32)))[..., :3].max() <= TOL16
+            assert np.array_equal(goth[..., 3].view(np.uint16), imh[..., 3].view(np.uint16) if alpha else np.full((h, w), 0x3c00, np.uint16))
+    # R8G8B8A8
+    raw = (np.random.default_rng(7).integers(0, 256, size=(h, w, 4))).astype(np.uint8)
+    fin = raw.astype(np.float32) / np.float32(255.0)
+    want = ol.rcas(fin, ol.rcas_con(0.25), False, denoise=denoise, alpha=alpha)
+    if square:
+        want[..., :3] = want[..., :3] * want[..., :3]
+    wq = _q(want[..., :3], 8)
+    out = torch.zeros((h, w + (-w) % 2, 4), dtype=torch.uint8, device="cuda")[:, :w]
+    src = torch.zeros((h, w + (-w) % 2, 4), dtype=torch.uint8, device="cuda")[:, :w]
+    src.copy_(torch.from_numpy(raw))
+    api.rcas(src, out, api.rcas_con(0.25), flags=fl)
+    torch.cuda.synchronize()
+    assert api.last_kernel().startswith("rcas_u8_packed"), api.last_kernel()
+    got8 = out.cpu().numpy()
+    assert np.abs(got8[..., :3].astype(np.int64) - wq.astype(np.int64)).max() <= 1
+    assert np.array_equal(got8[..., 3], raw[..., 3] if alpha else np.full((h, w), 255, np.uint8))
+
+
+def test_unorm8_production_kernels_within_one_code():
+    """R8G8B8A8_UNORM (what the sample renders into, FSR_Filter.cpp:72-73) at 2x takes the TMA-tiled EASU and the packed RCAS:
+    each within one code value of quantise(oracle(dequantise(input))), per kernel, at 1080p -> 4K."""
+    iw, ih, ow, oh = 1920, 1080, 3840, 2160
+    raw = np.floor(F.uniform(iw, ih, 12345) * 255.0 + 0.5).astype(np.uint8)
+    raw[::64, ::64] = 0
+    raw[32::64, 32::64] = 255
+    fin = raw.astype(np.float32) / np.float32(255.0)
+    din = torch.from_numpy(raw).cuda()
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.uint8, device="cuda")
+    out = torch.zeros_like(tmp)
+    api.easu(din, tmp, api.easu_con(iw, ih, iw, ih, ow, oh))
+    assert api.last_kernel().startswith("easu_u8_quad2x"), api.last_kernel()
+    api.rcas(tmp, out, api.rcas_con(0.25))
+    assert api.last_kernel().startswith("rcas_u8_packed"), api.last_kernel()
+    torch.cuda.synchronize()
+    e_got = tmp.cpu().numpy()
+    e_want = _q(ol.easu(fin, ow, oh)[..., :3], 8)
+    d = np.abs(e_got[..., :3].astype(np.int64) - e_want.astype(np.int64))
+    assert d.max() <= 1 and (d > 0).mean() < 0.10, (int(d.max()), float((d > 0).mean()))
+    assert (e_got[..., 3] == 255).all()
+    mid = e_got.astype(np.float32) / np.float32(255.0)
+    r_want = _q(ol.rcas(mid, ol.rcas_con(0.25))[..., :3], 8)
+    d = np.abs(out.cpu().numpy()[..., :3].astype(np.int64) - r_want.astype(np.int64))
+    assert d.max() <= 1, int(d.max())
+
+
+# ---- the fused EASU -> RCAS kernel (FSR1_FLAG_FUSED) -------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(96, 54, 192, 108), (33, 17, 66, 34), (130, 70, 260, 140), (5, 3, 10, 6), (1, 1, 2, 2), (200, 40, 400, 80)])
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_fused_kernel_is_bit_identical_to_the_two_kernel_path(shape, gen):
+    """FSR1_FLAG_FUSED at 2x RGBA16F: the intermediate stays in shared memory (rounded to fp16 exactly as the intermediate image
+    would be), so every output bit equals fsr1_easu + fsr1_rcas; `tmp` is not touched; row ranges (slabs) compose."""
+    iw, ih, ow, oh = shape
+    src = F.to_half(getattr(F, gen)(iw, ih, 91))
+    din = dev(src)
+    econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
+    tmp, want = empty_like_image(oh, ow, torch.float16), empty_like_image(oh, ow, torch.float16)
+    api.upscale(din, tmp, want, econ, rcon)
+    sentinel = torch.full((oh, (ow + 1) & ~1, 4), 7.0, dtype=torch.float16, device="cuda")[:, :ow]
+    got = empty_like_image(oh, ow, torch.float16)
+    api.upscale(din, sentinel, got, econ, rcon, flags=api.FLAG_FUSED)
+    assert api.last_kernel().startswith("fused_easu_rcas_h"), api.last_kernel()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert (sentinel == 7.0).all()                                   # no intermediate image
+    if oh >= 30:
+        parts = empty_like_image(oh, ow, torch.float16)
+        for (y0, y1) in ((0, oh // 3), (oh // 3, oh // 3 + 5), (oh // 3 + 5, oh)):
+            api.upscale(din, sentinel, parts, econ, rcon, y0=y0, y1=y1, flags=api.FLAG_FUSED)
+        torch.cuda.synchronize()
+        assert torch.equal(parts, want)
+    # other scales and options fall back to the two kernels (same results by construction)
+    api.upscale(din, tmp, got, econ, rcon, flags=api.FLAG_FUSED | api.FLAG_RCAS_CLAMP)
+    assert api.last_kernel().startswith("rcas_h_packed")
+
+
+@pytest.mark.parametrize("gen", ["uniform", "structured"])
+def test_fused_kernel_full_size_1080p_to_4k(gen):
+    iw, ih, ow, oh = 1920, 1080, 3840, 2160
+    src = F.to_half(getattr(F, gen)(iw, ih, 12345))
+    din = dev(src)
+    econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
+    tmp = torch.zeros((oh, ow, 4), dtype=torch.float16, device="cuda")
+    want, got = torch.zeros_like(tmp), torch.zeros_like(tmp)
+    api.upscale(din, tmp, want, econ, rcon)
+    api.upscale(din, tmp, got, econ, rcon, flags=api.FLAG_FUSED)
+    assert api.last_kernel().startswith("fused_easu_rcas_h"), api.last_kernel()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    e2e_check(got.cpu().numpy(), ol.rcas(ol.easu(src.astype(np.float32), ow, oh), ol.rcas_con(0.25)), ("fused", gen))
