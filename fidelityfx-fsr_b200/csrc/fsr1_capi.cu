@@ -5,6 +5,9 @@
 #include <new>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges "EASU" / "RCAS" / "FSR1" around the launches, as the sample's
+                               // user markers do (sample/src/DX12/FSR_Filter.cpp:118,128); no-ops unless a profiler is attached
+
 #include "../../include/fsr1_b200.h"
 #include "../../include/fsr1_host.h"
 #include "fsr1_common.cuh"
@@ -12,6 +15,11 @@
 using namespace fsr1;
 
 namespace {
+
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local int t_last_cuda = 0;
 thread_local const char* t_last_kernel = "";
@@ -151,6 +159,7 @@ int fsr1_easu_input_rows(const uint32_t con[16], uint32_t in_height, uint32_t y0
 
 int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16], uint32_t y0, uint32_t y1,
               uint32_t flags, void* stream) {
+  NvtxRange range("EASU");
   int rc;
   if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
   if (!con || (flags & ~kAllFlags)) return FSR1_ERR_INVALID_ARGUMENT;
@@ -193,6 +202,7 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
 
 int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4], uint32_t y0, uint32_t y1,
               uint32_t flags, void* stream) {
+  NvtxRange range("RCAS");
   int rc;
   if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
   if (!con || (flags & ~kAllFlags)) return FSR1_ERR_INVALID_ARGUMENT;
@@ -251,6 +261,7 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
 
 int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* out, const uint32_t easu_con[16],
                  const uint32_t rcas_con[4], uint32_t y0, uint32_t y1, uint32_t flags, void* stream) {
+  NvtxRange range("FSR1 upscale");
   if (!out) return FSR1_ERR_INVALID_ARGUMENT;
   if (y1 == 0) y1 = out->height;
   if (flags & FSR1_FLAG_NO_RCAS) return fsr1_easu(in, out, easu_con, y0, y1, flags, stream);

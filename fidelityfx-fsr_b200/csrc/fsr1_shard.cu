@@ -232,7 +232,7 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
     }
   }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) { fsr1_shard_destroy(s); return FSR1_ERR_CUDA; }  // flags are zero before anyone attaches
-  s->attached = world == 1;
+  s->attached = world == 1 || (flags & FSR1_SHARD_SKIP_HALO);
   *out_sh = s;
   return FSR1_OK;
 }

@@ -157,10 +157,12 @@ class ShardedUpscaler:
     Per frame: write the rank's input rows into input(slot), submit(slot), then wait(slot) before reading output(slot).
     All ranks construct with the same arguments and submit slots in the same order.
     `owned` / `out` are slot 0's tensors; upscale() is the one-frame convenience over slot 0.
+    halo="p2p" with world > 1 gathers the ranks' CUDA IPC handles through torch.distributed in the constructor (a collective:
+    every rank constructs at the same point); attach=False skips that for ranks living in one process (attach_local).
     """
 
     def __init__(self, in_w, in_h, out_w, out_h, world, rank, sharpness=0.25, dtype=None, device=None, flags=0, slots=1,
-                 halo=None, one_stream=False, group=None, skip_halo=False):
+                 halo=None, one_stream=False, group=None, skip_halo=False, attach=True):
         import torch
         self.rank, self.world, self.slots = int(rank), int(world), int(slots)
         self.in_w, self.in_h, self.out_w, self.out_h = in_w, in_h, out_w, out_h
@@ -180,13 +182,13 @@ class ShardedUpscaler:
         self._win0 = self.plan.window_rows(rank)[0]
         self._shard = None
         if halo == "p2p":
-            self._init_p2p(sharpness, dtype, one_stream, skip_halo)
+            self._init_p2p(sharpness, dtype, one_stream, skip_halo, attach)
         else:
             self._init_nccl(dtype)
         self.owned, self.out, self.window = self.inputs[0], self.outputs[0], self.windows[0]
 
     # ------------------------------------------------------------------------------------------ p2p (C ABI) data plane
-    def _init_p2p(self, sharpness, dtype, one_stream, skip_halo=False):
+    def _init_p2p(self, sharpness, dtype, one_stream, skip_halo=False, attach=True):
         import torch
         L = _lib.lib()
         fmt = {torch.float16: _lib.FORMAT_RGBA16F, torch.float32: _lib.FORMAT_RGBA32F, torch.uint8: _lib.FORMAT_RGBA8_UNORM}[dtype]
@@ -211,7 +213,7 @@ class ShardedUpscaler:
             self.inputs.append(_tensor_of(a, self.device))
             self.windows.append(_tensor_of(w, self.device))
             self.outputs.append(_tensor_of(b, self.device))
-        if self.world > 1:
+        if self.world > 1 and attach and not skip_halo:   # attach=False: the caller attaches (attach_local, several ranks in one process)
             self._attach_ipc()
 
     def _attach_ipc(self):

@@ -29,6 +29,7 @@ unsigned char* fsr1_emu_dynamic_smem() { return g_dynamic_smem; }
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_packed.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_f32.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_fused.cu"
+#include "../../fidelityfx-fsr_b200/csrc/fsr1_easu_f32.cu"
 
 using namespace fsr1;
 
@@ -295,4 +296,44 @@ extern "C" int emu_fused_h(const void* in, int iw, int ih, long long in_pitch, v
     pthread_barrier_destroy(&g_cta_barrier);
   }
   return 0;
+}
+
+// easu_f32_pairs_kernel<S>: any-scale EASU with fp32 arithmetic; storage 0 = RGBA32F (16-byte texels), 1 = RGBA16F.
+template <typename S>
+static int run_f32_pairs(const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh, long long out_pitch,
+                         const uint32_t* con, int y0, int y1, int max_ctas) {
+  constexpr int kB = Tex<S>::kBytes;
+  EasuParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, iw, ih, 0, ih};
+  p.out = ImgView{(unsigned char*)out, out_pitch, ow, oh, 0, oh};
+  memcpy(&p.c0x, &con[0], 4); memcpy(&p.c0y, &con[1], 4); memcpy(&p.c0z, &con[2], 4); memcpy(&p.c0w, &con[3], 4);
+  p.y0 = y0; p.y1 = y1;
+  if (!(p.c0x > 0.0f && p.c0x <= 1.0f && p.c0y > 0.0f && p.c0y <= 1.0f)) return -1;
+  int BW = max_footprint(ow, 0, kFTileW, p.c0x, p.c0z, kB == 8);
+  const int BH = max_footprint(y1, y0, kFTileH, p.c0y, p.c0w, false);
+  if (kB == 8) BW = (BW + 1) & ~1;
+  if (BW > 256 || BH > 256 || fpairs_smem_bytes<S>(BW, BH) > sizeof g_dynamic_smem) return -1;
+  const int tiles_x = (ow + kFTileW - 1) / kFTileW, n_tiles = tiles_x * ((y1 - y0 + kFTileH - 1) / kFTileH);
+  const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+  CUtensorMap tmap{(const unsigned char*)in, iw, ih, in_pitch, BW, BH, kB};
+  for (int b = 0; b < grid; b++) {
+    pthread_barrier_init(&g_cta_barrier, nullptr, (unsigned)kFThreads);
+    std::vector<std::thread> ts;
+    for (int t = 0; t < kFThreads; t++)
+      ts.emplace_back([=, &p, &tmap]() {
+        threadIdx = uint3{(unsigned)t, 0, 0};
+        blockIdx = uint3{(unsigned)b, 0, 0};
+        gridDim.x = (unsigned)grid;
+        blockDim.x = (unsigned)kFThreads;
+        easu_f32_pairs_kernel<S>(p, tmap, BW, BH, tiles_x, n_tiles);
+      });
+    for (auto& th : ts) th.join();
+    pthread_barrier_destroy(&g_cta_barrier);
+  }
+  return 0;
+}
+extern "C" int emu_easu_f32_pairs(int half_storage, const void* in, int iw, int ih, long long in_pitch, void* out, int ow, int oh,
+                                  long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
+  return half_storage ? run_f32_pairs<__half>(in, iw, ih, in_pitch, out, ow, oh, out_pitch, con, y0, y1, max_ctas)
+                      : run_f32_pairs<float>(in, iw, ih, in_pitch, out, ow, oh, out_pitch, con, y0, y1, max_ctas);
 }

@@ -309,3 +309,35 @@ def test_emulated_fused_kernel_is_bit_identical_to_the_two_kernel_path(size, cta
             assert rc == 0
             assert np.array_equal(out[y0:y1], want.view(np.uint16)[y0:y1]), (gen.__name__, y0, y1)
             assert not out[:y0].any() and not out[y1:].any()
+
+
+@pytest.mark.parametrize("shape", [(96, 54, 144, 81), (96, 54, 125, 70), (64, 64, 64, 64), (50, 20, 65, 26), (33, 17, 57, 31), (96, 54, 192, 81)])
+@pytest.mark.parametrize("half_storage", [0, 1])
+def test_emulated_any_scale_fp32_kernel(shape, half_storage):
+    """easu_f32_pairs_kernel: RGBA32F images (or fp32 arithmetic on RGBA16F storage, FSR1_FLAG_PRECISE) at scales other than 2x —
+    the structure of the fp16 any-scale kernel with packed-f32x2 tap weights; within 1e-5 of the oracle (fp32 storage) / one
+    rounding to half (fp16 storage), row ranges included."""
+    iw, ih, ow, oh = shape
+    con = (ctypes.c_uint32 * 16)(*ol.easu_con(iw, ih, ow, oh))
+    for gen in (F.uniform, F.structured):
+        src32 = gen(iw, ih, 31)
+        if half_storage:
+            src = np.ascontiguousarray(F.to_half(src32).view(np.uint16))
+            want = ol.easu(src.view(np.float16).astype(np.float32), ow, oh)
+            out = np.zeros((oh, ow, 4), np.uint16)
+        else:
+            src = np.ascontiguousarray(src32)
+            want = ol.easu(src, ow, oh)
+            out = np.zeros((oh, ow, 4), np.float32)
+        def run(y0, y1, ctas, dst):
+            rc = emu_lib().emu_easu_f32_pairs(half_storage, ctypes.c_void_p(src.ctypes.data), iw, ih, ctypes.c_longlong(src.strides[0]),
+                                              ctypes.c_void_p(dst.ctypes.data), ow, oh, ctypes.c_longlong(dst.strides[0]), con, y0, y1, ctas)
+            assert rc == 0
+        run(0, oh, 2, out)
+        got = out.view(np.float16).astype(np.float32) if half_storage else out
+        assert np.abs(got - want)[..., :3].max() <= (6e-4 if half_storage else 1e-5)
+        assert (got[..., 3] == 1.0).all()
+        part = np.zeros_like(out)
+        y0, y1 = oh // 3, 2 * oh // 3 + 1
+        run(y0, y1, 1, part)
+        assert np.array_equal(part[y0:y1], out[y0:y1]) and not part[:y0].any() and not part[y1:].any()

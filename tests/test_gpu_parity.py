@@ -77,8 +77,8 @@ def test_fp32_default_within_1e5(shape, gen):
     src = getattr(F, gen)(iw, ih, 32)
     want = ol.easu(src, ow, oh)
     got = gpu_easu(src, ow, oh)
-    if (2 * iw, 2 * ih) == (ow, oh):
-        assert api.last_kernel().startswith("easu_f32_quad2x"), api.last_kernel()
+    # a TMA-tiled kernel at every scale: the quad kernel at exactly 2x, the vertical-pair kernel otherwise (never easu_direct)
+    assert api.last_kernel().startswith("easu_f32_quad2x" if (2 * iw, 2 * ih) == (ow, oh) else "easu_f32_vpairs"), api.last_kernel()
     assert np.abs(got - want).max() <= TOL32
     alt = gpu_easu(src, ow, oh, api.FLAG_FORCE_DIRECT)
     assert api.last_kernel().startswith("easu_direct<f32,fast") and np.abs(alt - want).max() <= TOL32
@@ -242,6 +242,11 @@ def test_precise_flag_fp32_math_on_fp16_storage():
         assert np.all(got[..., 3] == 1.0)
         mid = gpu_rcas(got, 0.25)
         e2e_check(mid, ol.rcas(want, ol.rcas_con(0.25)), ("precise", gen), tight=True)
+        for (ow2, oh2) in ((300, 180), (261, 157)):                       # 1.5x and ~1.3x: the any-scale fp32-math kernel
+            want2 = ol.easu(src.astype(np.float32), ow2, oh2)
+            got2 = gpu_easu(src, ow2, oh2, api.FLAG_PRECISE)
+            assert api.last_kernel().startswith("easu_h16io_f32math_vpairs"), api.last_kernel()
+            assert np.abs(got2.astype(np.float32) - want2).max() <= 6e-4
 
 
 def e2e_check(got, want, what, tight=False):
@@ -513,7 +518,7 @@ def test_full_size_configs4_2160p_to_8k_in_8_slabs():
     iw, ih, ow, oh, world = 3840, 2160, 7680, 4320, 8
     src = F.to_half(F.structured(iw, ih, 4242))
     frame = torch.from_numpy(src).cuda()
-    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, slots=1, halo="p2p") for r in range(world)]
+    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, slots=1, halo="p2p", attach=False) for r in range(world)]
     for r, u in enumerate(ups):
         u.attach_local(ups[r - 1] if r > 0 else None, ups[r + 1] if r + 1 < world else None)
         assert u.plan.halo_bytes(r, iw, 8) == (2 if 0 < r < world - 1 else 1) * 61440

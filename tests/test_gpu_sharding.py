@@ -35,7 +35,7 @@ def plain_upscale(frame_t, ow, oh, sharp=0.25):
 def test_shards_in_one_process_equal_single_gpu(shape, world, one_stream):
     iw, ih, ow, oh = shape
     nslots, nframes = 2, 7
-    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, slots=nslots, halo="p2p", one_stream=one_stream) for r in range(world)]
+    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, slots=nslots, halo="p2p", one_stream=one_stream, attach=False) for r in range(world)]
     for r, u in enumerate(ups):
         u.attach_local(ups[r - 1] if r > 0 else None, ups[r + 1] if r + 1 < world else None)
     frames = [torch.from_numpy(F.to_half(F.uniform(iw, ih, 900 + t))).cuda() for t in range(nframes)]
@@ -75,11 +75,11 @@ def test_shards_in_one_process_equal_single_gpu(shape, world, one_stream):
 def test_shard_geometry_matches_python_plan_and_rejects_thin_slabs():
     for (ih, oh, world) in ((1080, 2160, 8), (2160, 4320, 8), (1440, 2160, 4), (1661, 2160, 3)):
         for r in (0, world // 2, world - 1):
-            u = F.ShardedUpscaler(64, ih, 96, oh, world, r, slots=1, halo="p2p")   # asserts SlabPlan == the C ABI's geometry inside
+            u = F.ShardedUpscaler(64, ih, 96, oh, world, r, slots=1, halo="p2p", attach=False)   # asserts SlabPlan == the C ABI's geometry inside
             assert u.info.halo_recv_bytes == u.plan.halo_bytes(r, 64, 8)
             u.close()
     with pytest.raises(F._lib.Fsr1Error):                # slabs of 1 input row cannot supply a 2-row halo: unsupported
-        F.ShardedUpscaler(64, 8, 128, 16, 8, 3, halo="p2p")
+        F.ShardedUpscaler(64, 8, 128, 16, 8, 3, halo="p2p", attach=False)
 
 
 def _ipc_worker(rank, world, port, shape, ndev, tmpdir, halo):

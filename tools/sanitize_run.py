@@ -35,7 +35,7 @@ for shape in ((150, 70, 300, 140), (150, 70, 225, 105)):
 # through the sharded data plane: 3 ranks on this device, halo by direct stores, two frames per slot
 for dt in (torch.float16, torch.float32):
     iw, ih, ow, oh, world = 160, 90, 320, 180 + 2, 3
-    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, dtype=dt, slots=2) for r in range(world)]
+    ups = [F.ShardedUpscaler(iw, ih, ow, oh, world, r, dtype=dt, slots=2, attach=False) for r in range(world)]
     for r, u in enumerate(ups):
         u.attach_local(ups[r - 1] if r else None, ups[r + 1] if r + 1 < world else None)
     s = torch.cuda.current_stream()
