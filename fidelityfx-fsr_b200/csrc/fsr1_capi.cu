@@ -25,6 +25,12 @@ thread_local int t_last_cuda = 0;
 thread_local const char* t_last_kernel = "";
 std::atomic<unsigned long long> g_launches{0};
 
+}  // namespace
+namespace fsr1 {
+void set_last_detail(int v) { t_last_cuda = v; }  // fsr1_shard_status: which wait timed out, reported through fsr1_last_cuda_error()
+}
+namespace {
+
 int cuda_fail(cudaError_t e) {
   t_last_cuda = (int)e;
   return FSR1_ERR_CUDA;

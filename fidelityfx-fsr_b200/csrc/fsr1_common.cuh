@@ -149,7 +149,19 @@ template <> struct Px<Unorm10> {
   }
 };
 
+// c / (2^n - 1) CORRECTLY ROUNDED without a division: q = c * (1/s) is off by one ulp for half of the 8-bit codes, and an ulp of
+// luma is enough to turn an exact tie between neighbouring texels (0/0 in FsrEasuSetF's length term, ffx_fsr1.h:298) into 1.0 instead
+// of 0.0 — the filter of a whole 2x2 cell block changes.  One FMA refinement makes q exact for every 8- and 10-bit code
+// (checked exhaustively, tests/test_constants.py).
+__device__ __forceinline__ float unorm_to_float(uint32_t c, float s, float rs) {
+  const float fc = (float)c;
+  const float q = fc * rs;
+  return fmaf(fmaf(-q, s, fc), rs, q);
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+void set_last_detail(int v);  // fsr1_capi.cu: detail word reported by fsr1_last_cuda_error()
 
 // launchers (defined in the .cu files, called from fsr1_capi.cu)
 cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name);

@@ -446,7 +446,7 @@ static cudaError_t launch_pairs_f32math(const EasuParams& p, cudaStream_t s, con
   if (kB == 8) BW = (BW + 1) & ~1;
   if (BW > 256 || BH > 256) return cudaErrorNotSupported;
   const size_t smem = fpairs_smem_bytes<S>(BW, BH);
-  if (smem > 110 * 1024) return cudaErrorNotSupported;  // two CTAs per SM
+  if (smem > 200 * 1024) return cudaErrorNotSupported;
   CUtensorMap tmap;
   CUresult r;
   if (kB == 16) {
@@ -470,7 +470,7 @@ static cudaError_t launch_pairs_f32math(const EasuParams& p, cudaStream_t s, con
     if (e != cudaSuccess) return e;
   }
   const int tiles_x = (p.out.w + kFTileW - 1) / kFTileW, n_tiles = tiles_x * ((p.y1 - p.y0 + kFTileH - 1) / kFTileH);
-  const int per_sm = 2;
+  const int per_sm = (size_t)2 * (smem + 1024) > 220 * 1024 ? 1 : 2;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
   easu_f32_pairs_kernel<S><<<grid, kFThreads, smem, s>>>(p, tmap, BW, BH, tiles_x, n_tiles);
   *name = nm;

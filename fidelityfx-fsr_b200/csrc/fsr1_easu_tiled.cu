@@ -340,11 +340,11 @@ template <int NW> struct __align__(128) QuadSmemU {
 
 template <int kBits> __device__ __forceinline__ float3 unorm_decode(uint32_t u) {
   if (kBits == 8) {
-    const float k = 1.0f / 255.0f;
-    return make_float3((float)(u & 255u) * k, (float)((u >> 8) & 255u) * k, (float)((u >> 16) & 255u) * k);
+    const float s = 255.0f, k = 1.0f / 255.0f;
+    return make_float3(unorm_to_float(u & 255u, s, k), unorm_to_float((u >> 8) & 255u, s, k), unorm_to_float((u >> 16) & 255u, s, k));
   }
-  const float k = 1.0f / 1023.0f;
-  return make_float3((float)(u & 1023u) * k, (float)((u >> 10) & 1023u) * k, (float)((u >> 20) & 1023u) * k);
+  const float s = 1023.0f, k = 1.0f / 1023.0f;
+  return make_float3(unorm_to_float(u & 1023u, s, k), unorm_to_float((u >> 10) & 1023u, s, k), unorm_to_float((u >> 20) & 1023u, s, k));
 }
 
 template <int NW, int MINB, int kBits>

@@ -65,15 +65,15 @@ template <int kBits> struct FmtUnorm {  // R8G8B8A8_UNORM (8) / R10G10B10A2_UNOR
   static __device__ __forceinline__ Row3 decode(Raw v) {
     Row3 o;
     if (kBits == 8) {
-      const float k = 1.0f / 255.0f;
-      o.r = __floats2half2_rn((float)(v.x & 255u) * k, (float)(v.y & 255u) * k);
-      o.g = __floats2half2_rn((float)((v.x >> 8) & 255u) * k, (float)((v.y >> 8) & 255u) * k);
-      o.b = __floats2half2_rn((float)((v.x >> 16) & 255u) * k, (float)((v.y >> 16) & 255u) * k);
+      const float s = 255.0f, k = 1.0f / 255.0f;
+      o.r = __floats2half2_rn(unorm_to_float(v.x & 255u, s, k), unorm_to_float(v.y & 255u, s, k));
+      o.g = __floats2half2_rn(unorm_to_float((v.x >> 8) & 255u, s, k), unorm_to_float((v.y >> 8) & 255u, s, k));
+      o.b = __floats2half2_rn(unorm_to_float((v.x >> 16) & 255u, s, k), unorm_to_float((v.y >> 16) & 255u, s, k));
     } else {
-      const float k = 1.0f / 1023.0f;
-      o.r = __floats2half2_rn((float)(v.x & 1023u) * k, (float)(v.y & 1023u) * k);
-      o.g = __floats2half2_rn((float)((v.x >> 10) & 1023u) * k, (float)((v.y >> 10) & 1023u) * k);
-      o.b = __floats2half2_rn((float)((v.x >> 20) & 1023u) * k, (float)((v.y >> 20) & 1023u) * k);
+      const float s = 1023.0f, k = 1.0f / 1023.0f;
+      o.r = __floats2half2_rn(unorm_to_float(v.x & 1023u, s, k), unorm_to_float(v.y & 1023u, s, k));
+      o.g = __floats2half2_rn(unorm_to_float((v.x >> 10) & 1023u, s, k), unorm_to_float((v.y >> 10) & 1023u, s, k));
+      o.b = __floats2half2_rn(unorm_to_float((v.x >> 20) & 1023u, s, k), unorm_to_float((v.y >> 20) & 1023u, s, k));
     }
     return o;
   }

@@ -231,6 +231,26 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
       return FSR1_ERR_CUDA;
     }
   }
+  if (world > 1) {
+    // Load every kernel a frame uses NOW.  CUDA loads kernels lazily, on first launch, and loading may synchronise the context: a
+    // first-use load issued while a flag-waiting kernel spins would wait for that kernel, which (several ranks in ONE process) may be
+    // waiting for work this very host thread has not submitted yet.  One dry frame on the zero-filled slot 0 (no halo protocol).
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, halo_push_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, halo_wait_kernel) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, credit_signal_kernel) != cudaSuccess) {
+      fsr1_shard_destroy(s);
+      return FSR1_ERR_CUDA;
+    }
+    fsr1_image win, out;
+    fsr1_shard_window(s, 0, &win);
+    fsr1_shard_output(s, 0, &out);
+    fsr1_image tmp0 = {s->tmp, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a, s->easu_rows.b - s->easu_rows.a, s->format, 0};
+    const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+    int rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, s->s_easu);
+    if (rc == FSR1_OK && (kflags & FSR1_FLAG_FUSED))  // the fused path may fall back to the two kernels for other frames: load those too
+      rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags & ~(uint32_t)FSR1_FLAG_FUSED, s->s_easu);
+    if (rc != FSR1_OK) { fsr1_shard_destroy(s); return rc; }
+  }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) { fsr1_shard_destroy(s); return FSR1_ERR_CUDA; }  // flags are zero before anyone attaches
   s->attached = world == 1 || (flags & FSR1_SHARD_SKIP_HALO);
   *out_sh = s;
@@ -385,7 +405,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
       ps[side].ready = pf + ready_idx(slot, side == kFromUp ? kFromDown : kFromUp);
     }
     if ((e = cudaStreamWaitEvent(s->s_comm, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
-    halo_push_kernel<<<2, 1024, 0, s->s_comm>>>(ps[kFromUp], ps[kFromDown], q, flags + kStatusIdx);
+    halo_push_kernel<<<2, 512, 0, s->s_comm>>>(ps[kFromUp], ps[kFromDown], q, flags + kStatusIdx);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     if ((e = cudaEventRecord(s->ev_push[slot], s->s_comm)) != cudaSuccess) return cuda_rc(e);
   }
@@ -454,6 +474,7 @@ int fsr1_shard_status(fsr1_shard* s) {
   DeviceGuard g(s->device);
   uint32_t st = 0;
   if (cudaMemcpy(&st, reinterpret_cast<uint32_t*>(s->arena) + kStatusIdx, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return FSR1_ERR_CUDA;
+  if (st != 0) fsr1::set_last_detail(1000 + (int)st + 10 * (int)s->rank);  // 1 / 2: push up / down starved of credit; 3 / 4: halo from above / below never came
   return st == 0 ? FSR1_OK : FSR1_ERR_TIMEOUT;
 }
 

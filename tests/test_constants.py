@@ -87,3 +87,18 @@ def test_host_header_compiles_as_c_and_matches(tmp_path):
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include", "compat"), str(src2), "-o",
                            str(tmp_path / "u"), "-lm"])
     assert subprocess.call([str(tmp_path / "u")]) == 0
+
+
+def test_unorm_decode_refinement_is_correctly_rounded_for_every_code():
+    """unorm_to_float (csrc/fsr1_common.cuh): q = c * (1/s) followed by one FMA refinement equals the correctly rounded c / s for
+    every 8- and 10-bit code (the plain product is an ulp off for half of the 8-bit codes, and an ulp of luma flips EASU's exact-tie
+    0/0 length term).  The device function itself runs in tests/test_emu.py (host build) and on the GPU."""
+    for s in (255, 1023):
+        c = np.arange(0, s + 1, dtype=np.float32)
+        want = (c / np.float32(s)).astype(np.float32)
+        k = np.float32(1.0) / np.float32(s)
+        q = (c * k).astype(np.float32)
+        assert (q != want).any()                      # the shortcut really is inexact
+        r = (c.astype(np.float64) - q.astype(np.float64) * np.float64(s)).astype(np.float32)          # fma(-q, s, c): exact
+        q2 = (r.astype(np.float64) * np.float64(k) + q.astype(np.float64)).astype(np.float32)         # fma(r, 1/s, q)
+        assert np.array_equal(q2, want)

@@ -23,8 +23,9 @@ api = F.api
 
 def plain_upscale(frame_t, ow, oh, sharp=0.25):
     ih, iw = frame_t.shape[:2]
-    tmp = torch.zeros((oh, ow, 4), dtype=frame_t.dtype, device=frame_t.device)
-    out = torch.zeros_like(tmp)
+    # rows padded to a 16-byte multiple like the shard's own buffers, so both take the same (TMA-tiled) kernels
+    tmp = torch.zeros((oh, (ow + 1) & ~1, 4), dtype=frame_t.dtype, device=frame_t.device)[:, :ow]
+    out = torch.zeros((oh, (ow + 1) & ~1, 4), dtype=frame_t.dtype, device=frame_t.device)[:, :ow]
     api.upscale(frame_t, tmp, out, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(sharp))
     return out
 

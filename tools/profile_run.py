@@ -1,5 +1,5 @@
 """A few launches of the two production kernels at the bench configuration, for ncu:
-   ncu --set full --clock-control none --import-source on -k regex:'easu_h|rcas_h' -s 4 -c 4 -o gpurun_out/prof python tools/profile_run.py
+   ncu --set full --clock-control none --import-source on -o gpurun_out/prof python tools/profile_run.py 2x 2
 """
 import os, sys
 import numpy as np, torch
@@ -18,5 +18,12 @@ for t in range(n):
 econ, rcon = api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)
 for a, t, b in sets:
     api.upscale(a, t, b, econ, rcon)
+if wl == "2x":
+    for a, t, b in sets:
+        api.upscale(a, t, b, econ, rcon, flags=api.FLAG_FUSED)          # the fused EASU->RCAS kernel
+    u8 = [torch.randint(0, 256, (ih, iw, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    t8, o8 = torch.empty((oh, ow, 4), dtype=torch.uint8, device="cuda"), torch.empty((oh, ow, 4), dtype=torch.uint8, device="cuda")
+    for a in u8:
+        api.upscale(a, t8, o8, econ, rcon)                                # R8G8B8A8: TMA-tiled EASU + packed RCAS
 torch.cuda.synchronize()
 print("done", api.launch_count(), api.last_kernel())
