@@ -19,8 +19,8 @@ DISPLAY = [
     (r"easu_h_quad2x_kernel<4, 7>", "easu_h_quad2x<4w,7/sm,tma2>"),
     (r"easu_u_quad2x_kernel<4, 6, 8>", "easu_u8_quad2x<4w,6/sm,tma2>"),
     (r"easu_h_pairs_kernel", "easu_h_vpairs<64x32,persistent,tma2>"),
-    (r"rcas_packed_kernel<fsr1::FmtHalf, false, 0>", "rcas_h_packed<2px,4rows,shfl60>"),
-    (r"rcas_packed_kernel<fsr1::FmtUnorm<8>, false, 0>", "rcas_u8_packed<2px,4rows,shfl60>"),
+    (r"rcas_packed_kernel<fsr1::FmtHalf, 0, 0>", "rcas_h_packed<2px,4rows,shfl60>"),
+    (r"rcas_packed_kernel<fsr1::FmtUnorm<8>, 0, 0>", "rcas_u8_packed<2px,4rows,shfl60>"),
     (r"fused_h_quad2x_kernel", "fused_easu_rcas_h_quad2x<4w,6/sm,tma2,strips>"),
     (r"easu_f32_quad2x_kernel<float", "easu_f32_quad2x<4w,4/sm,tma2,ffma2>"),
     (r"easu_f32_pairs_kernel<float", "easu_f32_vpairs<64x32,persistent,tma2,ffma2>"),
@@ -58,6 +58,8 @@ def main():
     want = WANT + [h for h in hdr if 'average_warps_issue_stalled' in h and 'per_issue_active.ratio' in h]
     traffic, issue = {}, {}
     for r in rows[2:]:
+        if 'fsr1::' not in r[idx['Kernel Name']]:
+            continue  # torch's own fill / random kernels of the driver script
         print('=====')
         for w in want:
             if w in idx:
