@@ -28,6 +28,10 @@ std::atomic<unsigned long long> g_launches{0};
 }  // namespace
 namespace fsr1 {
 void set_last_detail(int v) { t_last_cuda = v; }  // fsr1_shard_status: which wait timed out, reported through fsr1_last_cuda_error()
+static thread_local const HaloSync* t_sync = nullptr;
+static thread_local bool t_sync_used = false;
+void set_halo_sync(const HaloSync* hs) { t_sync = hs; t_sync_used = false; }
+bool halo_sync_consumed() { return t_sync_used; }
 }
 namespace {
 
@@ -191,7 +195,12 @@ int fsr1_easu(const fsr1_image* in, const fsr1_image* out, const uint32_t con[16
     e = launch_easu_href(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     if (flags & FSR1_FLAG_PRECISE) e = launch_easu_h_precise(p, s, &name);
-    if (e == cudaErrorNotSupported) e = launch_easu_h_tiled(p, s, &name);
+    if (e == cudaErrorNotSupported) {
+      if (t_sync) p.sync = *t_sync;  // sharded frame: the neighbour hand-shake rides inside the kernel
+      e = launch_easu_h_tiled(p, s, &name);
+      if (e == cudaSuccess && t_sync) t_sync_used = true;
+      p.sync = HaloSync{};
+    }
   } else if (in->format == FSR1_FORMAT_RGBA32F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
     e = launch_easu_f32_tiled(p, s, &name);
   } else if ((in->format == FSR1_FORMAT_RGBA8_UNORM || in->format == FSR1_FORMAT_RGB10A2_UNORM) && !exact &&
@@ -290,7 +299,9 @@ int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* 
     p.c0x = as_float(easu_con[0]); p.c0y = as_float(easu_con[1]); p.c0z = as_float(easu_con[2]); p.c0w = as_float(easu_con[3]);
     p.y0 = (int)y0; p.y1 = (int)y1;
     const char* name = "";
+    if (t_sync) p.sync = *t_sync;
     const cudaError_t e = launch_fused_h(p, rcas_con[1], 0, static_cast<cudaStream_t>(stream), &name);
+    if (e == cudaSuccess && t_sync) t_sync_used = true;
     if (e == cudaSuccess) {
       t_last_kernel = name;
       g_launches.fetch_add(1);

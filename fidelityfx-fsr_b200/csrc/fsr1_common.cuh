@@ -23,10 +23,24 @@ __host__ __device__ __forceinline__ bool row_stored(const ImgView& im, int y) {
   return y >= im.row0 && y < im.row0 + im.rows && y >= 0 && y < im.h;
 }
 
+// Row-slab sharding (fsr1_shard.cu): the neighbour hand-shake of a frame folded INTO the kernel that reads the input window, so the
+// frame costs no extra launch on the critical stream.  ready[side]: flags in this GPU's memory the neighbours set (release.sys) when
+// the halo rows of use `seq` of this window are in place — every CTA's thread 0 acquires them before the CTA's first load.
+// credit[side]: flags in the NEIGHBOURS' memory the last CTA to finish sets: "use `seq` of my window has been read, you may overwrite
+// your rows in it".  All pointers null outside the sharded path.
+struct HaloSync {
+  const uint32_t* ready[2];
+  uint32_t* credit[2];
+  uint32_t* counter;  // CTAs finished (device memory, zero between launches)
+  uint32_t* status;   // != 0: a wait timed out
+  uint32_t seq;
+};
+
 struct EasuParams {
   ImgView in, out;
   float c0x, c0y, c0z, c0w;  // con0 of FsrEasuCon: scale.xy, offset.zw
   int y0, y1;                // output rows [y0,y1)
+  HaloSync sync = {};
 };
 
 struct RcasParams {
@@ -154,14 +168,74 @@ template <> struct Px<Unorm10> {
 // of 0.0 — the filter of a whole 2x2 cell block changes.  One FMA refinement makes q exact for every 8- and 10-bit code
 // (checked exhaustively, tests/test_constants.py).
 __device__ __forceinline__ float unorm_to_float(uint32_t c, float s, float rs) {
-  const float fc = (float)c;
+  const float fc = __uint_as_float(0x4b000000u | c) - 8388608.0f;  // (float)c for c < 2^23 without the conversion pipe: 2^23 + c, minus 2^23
   const float q = fc * rs;
   return fmaf(fmaf(-q, s, fc), rs, q);
 }
 
+// ---- flags shared between GPUs (system scope) --------------------------------------------------------------------------
+#ifdef FSR1_CPU_EMU
+inline void halo_sync_begin(const HaloSync&) {}
+inline void halo_sync_end(const HaloSync&) {}
+#else
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a dead neighbour sets an error word instead of hanging the GPU
+// wait until *flag >= want (sequence numbers, wrap-safe); false on timeout
+__device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t want) {
+  if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
+  const unsigned long long t0 = global_ns();
+  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+    if (global_ns() - t0 > kSpinTimeoutNs) return false;
+    __nanosleep(50);
+  }
+  return true;
+}
+// first thing a kernel does (all threads): the halo rows of this use of the window are in place
+__device__ __forceinline__ void halo_sync_begin(const HaloSync& hs) {
+  if (hs.ready[0] || hs.ready[1]) {
+    if (threadIdx.x == 0) {
+      if (hs.ready[0] && !spin_until(hs.ready[0], hs.seq)) atomicExch(hs.status, 3u);
+      if (hs.ready[1] && !spin_until(hs.ready[1], hs.seq)) atomicExch(hs.status, 4u);
+    }
+    __syncthreads();
+  }
+}
+// last thing (all threads, after the CTA's last read of the window): the last CTA of the grid tells the neighbours
+__device__ __forceinline__ void halo_sync_end(const HaloSync& hs) {
+  if (hs.counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(hs.counter, 1u) == gridDim.x * gridDim.y - 1) {
+        atomicExch(hs.counter, 0u);
+        __threadfence();
+        if (hs.credit[0]) st_release_sys(hs.credit[0], hs.seq);
+        if (hs.credit[1]) st_release_sys(hs.credit[1], hs.seq);
+      }
+    }
+  }
+}
+#endif
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 void set_last_detail(int v);  // fsr1_capi.cu: detail word reported by fsr1_last_cuda_error()
+// fsr1_shard.cu -> fsr1_capi.cu: the hand-shake the NEXT EASU (or fused) launch on this thread should carry; consumed() tells whether the
+// kernel that was launched took it (the TMA-tiled fp16 kernels do; otherwise the shard falls back to its own tiny wait / signal kernels)
+void set_halo_sync(const HaloSync* hs);
+bool halo_sync_consumed();
 
 // launchers (defined in the .cu files, called from fsr1_capi.cu)
 cudaError_t launch_easu_direct(const EasuParams& p, int format, bool exact, cudaStream_t s, const char** name);

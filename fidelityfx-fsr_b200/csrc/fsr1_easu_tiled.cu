@@ -163,6 +163,7 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
     mbar_fence_init();
   }
   __syncthreads();
+  halo_sync_begin(p.sync);
   // box origin of tile t = first tap column/row of its first pixel; the column is rounded down to even because
   // TMA traps unless the box starts on a 16-byte boundary (2 texels)
   auto origin = [&](int t, int& ox0, int& oy0, int& fx0, int& fy0) {
@@ -249,6 +250,7 @@ easu_h_pairs_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tmap
   }
   __syncthreads();  // L, S and this tile buffer are free again
   }  // persistent tile loop
+  halo_sync_end(p.sync);
 }
 
 // =======================================================================================================
@@ -275,6 +277,7 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     mbar_fence_init();
   }
   __syncthreads();
+  halo_sync_begin(p.sync);
   // tile (tx, ty): cells k in [32 tx - 1, +32), m in [mbase + kCY ty, +kCY); box origin = (first cell) - 1.
   // Tile coordinates advance incrementally: one division per kernel instead of one per tile and thread.
   int t = blockIdx.x;
@@ -323,6 +326,7 @@ easu_h_quad2x_kernel(const EasuParams p, const __grid_constant__ CUtensorMap tma
     }
     __syncthreads();  // L, S and this tile buffer are free again
   }
+  halo_sync_end(p.sync);
 }
 
 // ---- 2x EASU for the UNORM formats the sample renders into (sample/src/DX12/FSR_Filter.cpp:72-73) -------------------

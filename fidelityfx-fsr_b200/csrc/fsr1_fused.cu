@@ -39,6 +39,7 @@ struct FusedParams {
   int y0, y1;          // output rows
   uint32_t sharp_h2;   // RCAS con.y
   int n_strips;
+  HaloSync sync = {};
 };
 
 template <int NW> struct FusedCfg {
@@ -114,6 +115,7 @@ fused_h_quad2x_kernel(const FusedParams p, const __grid_constant__ CUtensorMap t
     mbar_fence_init();
   }
   __syncthreads();
+  halo_sync_begin(p.sync);
   FusedIter<CY> iter;
   iter.init(p, blockIdx.x, gridDim.x);
   FusedStep cur, nxt;
@@ -211,6 +213,7 @@ fused_h_quad2x_kernel(const FusedParams p, const __grid_constant__ CUtensorMap t
     cur = nxt;
     has = hasn;
   }
+  halo_sync_end(p.sync);
 }
 
 #ifndef FSR1_CPU_EMU
@@ -232,7 +235,7 @@ cudaError_t launch_fused_h(const EasuParams& e, uint32_t sharp_h2, int clamp, cu
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorNotSupported;
   FusedParams p;
-  p.in = e.in; p.out = e.out; p.y0 = e.y0; p.y1 = e.y1; p.sharp_h2 = sharp_h2;
+  p.in = e.in; p.out = e.out; p.y0 = e.y0; p.y1 = e.y1; p.sharp_h2 = sharp_h2; p.sync = e.sync;
   // output pairs (2k, 2k+1), k = 0 .. (w-1)/2, 31 per strip
   p.n_strips = ((e.out.w + 1) / 2 + kStripCells - 1) / kStripCells;
   const long long units = (long long)p.n_strips * ((e.y1 - e.y0 + 1) / 2);

@@ -6,14 +6,16 @@
 // by pointer).  The OUTPUT image is cut into `world` row slabs; rank k owns input rows [k inH/world, (k+1) inH/world)
 // and needs 2-3 more rows each side (the EASU footprint of its slab plus the one-row apron RCAS reads).
 //
-// Data plane per frame (no NCCL, no host round trip, no collective):
-//   comm stream   halo_push_kernel: block 0 copies my top rows into the upper neighbour's window (its bottom halo),
-//                 block 1 my bottom rows into the lower neighbour's; 128-bit stores over NVLink, __threadfence_system,
-//                 then a release store of the frame's sequence number into the neighbour's `ready` flag.
-//   EASU stream   halo_wait_kernel (2 lanes spin on MY `ready` flags, acquire loads of local memory) -> EASU over the
-//                 slab +-1 row -> credit_signal_kernel (release store of the sequence number into the neighbours'
-//                 `credit` flags: "your rows in my window may be overwritten").
-//   RCAS stream   RCAS of frame i overlaps EASU of frame i+1 exactly as api.FramePipeline does on one GPU.
+// Data plane per frame (no NCCL, no host round trip, no collective, and NO extra launch on the streams the big kernels use):
+//   comm stream   halo_push_kernel, 2 x 8 one-warp CTAs on a HIGH-PRIORITY stream (a 32-thread CTA fits beside the seven resident EASU
+//   (high prio)   CTAs of an SM and is dispatched ahead of pending RCAS CTAs): half of them copy my top rows into the upper neighbour's
+//                 window (its bottom halo), the others my bottom rows into the lower neighbour's — 128-bit stores over NVLink,
+//                 __threadfence_system, then a release store of the frame's sequence number into the neighbour's `ready` flag.
+//   EASU stream   the EASU (or fused) kernel itself carries the hand-shake (HaloSync, fsr1_common.cuh): every CTA's thread 0
+//                 acquires MY `ready` flags before the CTA's first load, the last CTA to finish release-stores the sequence
+//                 number into the neighbours' `credit` flags ("your rows in my window may be overwritten").  Kernels without
+//                 that hook (UNORM, fp32, direct) get the same protocol from two one-warp kernels around them.
+//   RCAS stream   RCAS of frame i overlaps EASU of frame i+1 exactly as on one GPU.
 // Flow control is by sequence numbers in device memory, so it is independent of host timing on either side: a push
 // for the q-th use of a slot waits for credit q-1, EASU of use q waits for ready q.  Every spin is bounded (a wall
 // clock timeout sets an error word instead of hanging the GPU).
@@ -25,39 +27,20 @@
 
 namespace {
 
+using fsr1::spin_until;
+using fsr1::st_release_sys;
+
 constexpr uint32_t kFlagBytes = 4096;          // flags page at the start of the arena
 constexpr uint32_t kMaxSlots = 128;
-constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s
 
 enum { kFromUp = 0, kFromDown = 1 };
 // flag word index inside an arena's flags page
 __host__ __device__ inline uint32_t ready_idx(uint32_t slot, int from) { return slot * 4 + from; }
 __host__ __device__ inline uint32_t credit_idx(uint32_t slot, int from) { return slot * 4 + 2 + from; }
 constexpr uint32_t kStatusIdx = kMaxSlots * 4;  // != 0: a spin timed out (value = 1 + which)
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// wait until *flag >= want (sequence numbers, wrap-safe); false on timeout
-__device__ bool spin_until(const uint32_t* flag, uint32_t want) {
-  if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
-  const unsigned long long t0 = global_ns();
-  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
-    if (global_ns() - t0 > kSpinTimeoutNs) return false;
-    __nanosleep(50);
-  }
-  return true;
-}
+__host__ __device__ inline uint32_t counter_idx(uint32_t slot) { return kStatusIdx + 1 + slot; }  // CTAs of the slot's EASU that finished
+__host__ __device__ inline uint32_t push_cnt_idx(uint32_t slot, int side) { return kStatusIdx + 1 + kMaxSlots + slot * 2 + side; }  // push parts done
+constexpr int kPushParts = 8;  // one-warp CTAs per direction
 
 struct PushSide {
   const uint4* src;        // my rows (local)
@@ -65,30 +48,53 @@ struct PushSide {
   uint32_t n16;            // 16-byte units
   const uint32_t* credit;  // local: the neighbour has finished reading the previous use of this slot
   uint32_t* ready;         // peer: "your halo rows for use q are in place"
+  uint32_t* parts_done;    // local: one-warp CTAs of this push that have finished
 };
 
-__global__ void __launch_bounds__(1024) halo_push_kernel(const PushSide up, const PushSide down, const uint32_t q, uint32_t* status) {
-  const PushSide s = blockIdx.x == 0 ? up : down;
+// kPushParts one-warp CTAs per direction (blockIdx.x / kPushParts = 0: up, 1: down), each moving 1/kPushParts of the rows.  32 threads
+// and < 32 registers: such a CTA fits into what seven resident EASU CTAs leave of an SM, so a push never waits for a big kernel to
+// finish.  Stores over NVLink are fire-and-forget; two 16-byte loads per lane are kept in flight.  The last part to finish (counter in
+// local memory) publishes the sequence number.
+__global__ void __launch_bounds__(32) halo_push_kernel(const PushSide up, const PushSide down, const uint32_t q, uint32_t* status) {
+  const int side = blockIdx.x / kPushParts, part = blockIdx.x - side * kPushParts;
+  const PushSide s = side == 0 ? up : down;
   if (!s.dst) return;
-  __shared__ int ok;
+  int ok = 1;
   if (threadIdx.x == 0) {
     ok = spin_until(s.credit, q - 1) ? 1 : 0;
-    if (!ok) atomicExch(status, 1u + blockIdx.x);
+    if (!ok) atomicExch(status, 1u + side);
   }
-  __syncthreads();
-  if (!ok) return;
-  for (uint32_t i = threadIdx.x; i < s.n16; i += blockDim.x) s.dst[i] = s.src[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) st_release_sys(s.ready, q);
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (ok) {
+    const uint32_t per = (s.n16 + kPushParts - 1) / kPushParts, first = part * per;
+    const uint32_t end = first + per < s.n16 ? first + per : s.n16;
+    const uint32_t t0 = first + threadIdx.x;
+    uint32_t left = end > t0 ? (end - t0 + 31) / 32 : 0;  // 16-byte units this lane moves
+    const uint4* src = s.src + t0;
+    uint4* dst = s.dst + t0;
+#pragma unroll 1
+    for (; left >= 2; left -= 2, src += 64, dst += 64) {
+      const uint4 a = src[0], b = src[32];
+      dst[0] = a;
+      dst[32] = b;
+    }
+    if (left) dst[0] = src[0];
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (threadIdx.x == 0 && atomicAdd(s.parts_done, 1u) == kPushParts - 1) {  // last part (a timed-out push publishes nothing)
+    atomicExch(s.parts_done, 0u);
+    __threadfence_system();  // acquire side of the counter: the other parts' stores (fenced before their increment) precede the flag
+    if (ok) st_release_sys(s.ready, q);
+  }
 }
 
-__global__ void halo_wait_kernel(const uint32_t* ready_up, const uint32_t* ready_down, const uint32_t q, uint32_t* status) {
+__global__ void __launch_bounds__(32) halo_wait_kernel(const uint32_t* ready_up, const uint32_t* ready_down, const uint32_t q, uint32_t* status) {
   const uint32_t* f = threadIdx.x == 0 ? ready_up : (threadIdx.x == 1 ? ready_down : nullptr);
   if (f && !spin_until(f, q)) atomicExch(status, 3u + threadIdx.x);
 }
 
-__global__ void credit_signal_kernel(uint32_t* credit_up, uint32_t* credit_down, const uint32_t q) {
+__global__ void __launch_bounds__(32) credit_signal_kernel(uint32_t* credit_up, uint32_t* credit_down, const uint32_t q) {
   uint32_t* f = threadIdx.x == 0 ? credit_up : (threadIdx.x == 1 ? credit_down : nullptr);
   if (f) st_release_sys(f, q);
 }
@@ -127,6 +133,7 @@ struct fsr1_shard {
   cudaStream_t s_comm, s_easu, s_rcas;
   cudaEvent_t ev_in[kMaxSlots], ev_push[kMaxSlots], ev_easu[kMaxSlots], ev_rcas[kMaxSlots];
   bool attached;
+  bool inkernel_sync;  // the EASU / fused kernel of this configuration carries the hand-shake itself (HaloSync)
 };
 
 namespace {
@@ -212,11 +219,13 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
   s->tmp_slot_stride = (uint64_t)(s->easu_rows.b - s->easu_rows.a) * s->out_pitch;
   s->out_slot_stride = (uint64_t)(s->out_rows.b - s->out_rows.a) * s->out_pitch;
   cudaError_t e;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lowest = most urgent
   // cudaMalloc (not a pool / VMM allocation): the arena must be exportable through cudaIpcGetMemHandle
   if ((e = cudaMalloc((void**)&s->arena, s->arena_bytes)) != cudaSuccess || (e = cudaMemset(s->arena, 0, s->arena_bytes)) != cudaSuccess ||
       (e = cudaMalloc((void**)&s->tmp, s->tmp_slot_stride * slots)) != cudaSuccess ||
       (e = cudaMalloc((void**)&s->out, s->out_slot_stride * slots)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&s->s_comm, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&s->s_easu, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&s->s_rcas, cudaStreamNonBlocking)) != cudaSuccess) {
     fsr1_shard_destroy(s);
@@ -246,7 +255,11 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
     fsr1_shard_output(s, 0, &out);
     fsr1_image tmp0 = {s->tmp, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a, s->easu_rows.b - s->easu_rows.a, s->format, 0};
     const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+    const fsr1::HaloSync none = {};
+    fsr1::set_halo_sync(&none);  // does this configuration's kernel take the hand-shake? (null pointers: a no-op inside the kernel)
     int rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, s->s_easu);
+    s->inkernel_sync = fsr1::halo_sync_consumed();
+    fsr1::set_halo_sync(nullptr);
     if (rc == FSR1_OK && (kflags & FSR1_FLAG_FUSED))  // the fused path may fall back to the two kernels for other frames: load those too
       rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags & ~(uint32_t)FSR1_FLAG_FUSED, s->s_easu);
     if (rc != FSR1_OK) { fsr1_shard_destroy(s); return rc; }
@@ -392,7 +405,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   if (up || down) {
     PushSide ps[2];
     for (int side = 0; side < 2; side++) {
-      ps[side] = PushSide{nullptr, nullptr, 0, nullptr, nullptr};
+      ps[side] = PushSide{nullptr, nullptr, 0, nullptr, nullptr, nullptr};
       const bool has = side == kFromUp ? up : down;
       if (!has) continue;
       const Rows r = s->send[side];
@@ -401,51 +414,58 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
       ps[side].dst = reinterpret_cast<uint4*>(window_of(s, s->peer[side], slot) + (uint64_t)(r.a - s->peer_win0[side]) * s->pitch);
       ps[side].n16 = (uint32_t)((uint64_t)(r.b - r.a) * s->pitch / 16);
       ps[side].credit = flags + credit_idx(slot, side);
+      ps[side].parts_done = flags + push_cnt_idx(slot, side);
       // I am the neighbour's lower (upper) peer when I push up (down)
       ps[side].ready = pf + ready_idx(slot, side == kFromUp ? kFromDown : kFromUp);
     }
     if ((e = cudaStreamWaitEvent(s->s_comm, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
-    halo_push_kernel<<<2, 512, 0, s->s_comm>>>(ps[kFromUp], ps[kFromDown], q, flags + kStatusIdx);
+    halo_push_kernel<<<2 * kPushParts, 32, 0, s->s_comm>>>(ps[kFromUp], ps[kFromDown], q, flags + kStatusIdx);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     if ((e = cudaEventRecord(s->ev_push[slot], s->s_comm)) != cudaSuccess) return cuda_rc(e);
   }
   if ((e = cudaStreamWaitEvent(se, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
   if (q > 1 && !one_stream && (e = cudaStreamWaitEvent(se, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);  // the slot's intermediate is free
-  if (up || down) {
-    halo_wait_kernel<<<1, 32, 0, se>>>(up ? flags + ready_idx(slot, kFromUp) : nullptr, down ? flags + ready_idx(slot, kFromDown) : nullptr, q,
-                                       flags + kStatusIdx);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-  }
   fsr1_image win, out;
   fsr1_shard_window(s, slot, &win);
   fsr1_shard_output(s, slot, &out);
   fsr1_image tmp = make_img(s->tmp + (uint64_t)slot * s->tmp_slot_stride, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a,
                             s->easu_rows.b - s->easu_rows.a, s->format);
   const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
-  uint32_t* cu = up ? reinterpret_cast<uint32_t*>(s->peer[kFromUp]) + credit_idx(slot, kFromDown) : nullptr;
-  uint32_t* cd = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
-  if (kflags & FSR1_FLAG_FUSED) {
-    // one kernel per frame where the fused EASU->RCAS kernel applies (fsr1_upscale falls back to the two kernels otherwise);
-    // consecutive frames overlap on the two streams alternately
-    cudaStream_t sf = one_stream ? se : ((q + slot) & 1 ? sr : se);
-    if (sf != se) {  // order the frame's stream after the halo wait / input event recorded on se
-      if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
-      if ((e = cudaStreamWaitEvent(sf, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
-    }
-    int rc = fsr1_upscale(&win, &tmp, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, sf);
-    if (rc != FSR1_OK) return rc;
-    if (up || down) {
-      credit_signal_kernel<<<1, 32, 0, sf>>>(cu, cd, q);
-      if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    }
-    if ((e = cudaEventRecord(s->ev_rcas[slot], sf)) != cudaSuccess) return cuda_rc(e);
-    return FSR1_OK;
+  fsr1::HaloSync hs = {};
+  hs.ready[kFromUp] = up ? flags + ready_idx(slot, kFromUp) : nullptr;
+  hs.ready[kFromDown] = down ? flags + ready_idx(slot, kFromDown) : nullptr;
+  hs.credit[kFromUp] = up ? reinterpret_cast<uint32_t*>(s->peer[kFromUp]) + credit_idx(slot, kFromDown) : nullptr;
+  hs.credit[kFromDown] = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
+  hs.counter = flags + counter_idx(slot);
+  hs.status = flags + kStatusIdx;
+  hs.seq = q;
+  const bool shake = up || down, inkernel = shake && s->inkernel_sync;
+  const bool fused = (kflags & FSR1_FLAG_FUSED) != 0;
+  // fused: one kernel per frame (fsr1_upscale falls back to the two kernels where the fused one does not apply), consecutive frames
+  // alternate between the two streams; two-kernel path: EASU on se, RCAS on sr
+  cudaStream_t sk = (fused && !one_stream && ((q + slot) & 1)) ? sr : se;
+  if (sk != se) {  // the frame's stream starts after the input / intermediate events waited on se
+    if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
+    if ((e = cudaStreamWaitEvent(sk, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
   }
-  int rc = fsr1_easu(&win, &tmp, s->econ, s->easu_rows.a, s->easu_rows.b, kflags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, se);
-  if (rc != FSR1_OK) return rc;
-  if (up || down) {
-    credit_signal_kernel<<<1, 32, 0, se>>>(cu, cd, q);
+  if (shake && !inkernel) {
+    halo_wait_kernel<<<1, 32, 0, sk>>>(hs.ready[kFromUp], hs.ready[kFromDown], q, flags + kStatusIdx);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+  }
+  if (inkernel) fsr1::set_halo_sync(&hs);
+  int rc = fused ? fsr1_upscale(&win, &tmp, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, sk)
+                 : fsr1_easu(&win, &tmp, s->econ, s->easu_rows.a, s->easu_rows.b, kflags & ~(uint32_t)FSR1_FLAG_OUTPUT_SQUARE, sk);
+  const bool took = inkernel && fsr1::halo_sync_consumed();
+  fsr1::set_halo_sync(nullptr);
+  if (rc != FSR1_OK) return rc;
+  if (inkernel && !took) return FSR1_ERR_UNSUPPORTED;  // cannot happen: the capability was probed with this configuration
+  if (shake && !inkernel) {
+    credit_signal_kernel<<<1, 32, 0, sk>>>(hs.credit[kFromUp], hs.credit[kFromDown], q);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+  }
+  if (fused) {
+    if ((e = cudaEventRecord(s->ev_rcas[slot], sk)) != cudaSuccess) return cuda_rc(e);
+    return FSR1_OK;
   }
   if (!one_stream) {
     if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
