@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     halo_mode = args.halo if world > 1 else "p2p"
     kflags = api.FLAG_FUSED if args.fused else 0
     up = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo=halo_mode,
-                           one_stream=args.no_pipeline, flags=kflags)
+                           one_stream=args.no_pipeline, flags=kflags, trace=args.trace and world > 1)
     plan = up.plan
     o0, o1 = plan.owned_in_rows(rank)
     e0, e1 = plan.easu_rows(rank)
@@ -356,6 +356,21 @@ def run_ours(args, rank, world, local_rank):
     launches = api.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     up.status()
+    if args.trace and world > 1 and halo_mode == "p2p":
+        tr = up.trace().astype(np.int64)
+        if len(tr) > 8:
+            tr = tr[4:-2]
+            wait = (tr[:, 1] - tr[:, 0]) / 1e3
+            kern = (tr[:, 2] - tr[:, 0]) / 1e3
+            period = np.diff(tr[:, 2]) / 1e3
+            lead_u = (tr[:, 0] - tr[:, 4]) / 1e3      # my push (up) published this long BEFORE my own EASU of the same frame started
+            lead_d = (tr[:, 0] - tr[:, 6]) / 1e3
+            pdur_u, pdur_d = (tr[:, 4] - tr[:, 3]) / 1e3, (tr[:, 6] - tr[:, 5]) / 1e3
+            def st(a):
+                a = a[np.isfinite(a)]
+                return "med %.1f p90 %.1f max %.1f" % (np.median(a), np.percentile(a, 90), a.max()) if len(a) else "-"
+            sys.stderr.write("[trace rank %d] us: halo wait inside EASU %s | EASU kernel (wait+work) %s | frame period %s | push duration up %s down %s | "
+                             "own push published before own EASU start: up %s down %s\n" % (rank, st(wait), st(kern), st(period), st(pdur_u), st(pdur_d), st(lead_u), st(lead_d)))
     value = total_out_px * K / (ms * 1e-3) / 1e6
     peak, peak_src = load_peaks()
 
@@ -624,6 +639,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--fused", action="store_true", help="FSR1_FLAG_FUSED: EASU and RCAS in one kernel (intermediate in shared memory); roofline against bpp*(Pin+Pout)")
+    ap.add_argument("--trace", action="store_true", help="multi-GPU p2p: print device-timestamp statistics of the halo hand-shake per rank (stderr)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo data plane: direct NVLink stores through the C ABI (default) or NCCL send/recv")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

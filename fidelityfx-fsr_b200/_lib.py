@@ -10,7 +10,7 @@ FSR1_OK = 0
 FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_RGB10A2_UNORM = 1, 2, 3, 4
 FLAG_RCAS_CLAMP, FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_H_REFERENCE, FLAG_PRECISE = 1, 2, 4, 8, 16, 32
 FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE, FLAG_FUSED = 64, 128, 256, 512
-SHARD_ONE_STREAM, SHARD_SKIP_HALO, SHARD_HANDLE_BYTES = 1 << 16, 1 << 17, 64
+SHARD_ONE_STREAM, SHARD_SKIP_HALO, SHARD_TRACE, SHARD_HANDLE_BYTES = 1 << 16, 1 << 17, 1 << 18, 64
 
 # every symbol include/fsr1_b200.h declares
 SYMBOLS = ["fsr1_easu", "fsr1_rcas", "fsr1_easu_input_rows", "fsr1_upscale", "fsr1_context_create",
@@ -19,7 +19,7 @@ SYMBOLS = ["fsr1_easu", "fsr1_rcas", "fsr1_easu_input_rows", "fsr1_upscale", "fs
            "fsr1_last_cuda_error", "fsr1_launch_count", "fsr1_last_kernel_name", "fsr1_srtm", "fsr1_lfga", "fsr1_tepd",
            "fsr1_shard_create", "fsr1_shard_destroy", "fsr1_shard_geometry", "fsr1_shard_export", "fsr1_shard_attach",
            "fsr1_shard_attach_local", "fsr1_shard_input", "fsr1_shard_window", "fsr1_shard_output", "fsr1_shard_arena",
-           "fsr1_shard_submit", "fsr1_shard_wait", "fsr1_shard_status"]
+           "fsr1_shard_submit", "fsr1_shard_wait", "fsr1_shard_status", "fsr1_shard_trace"]
 
 
 class Image(ctypes.Structure):
@@ -87,6 +87,7 @@ def lib():
     L.fsr1_shard_submit.argtypes = [vp, u32, vp]
     L.fsr1_shard_wait.argtypes = [vp, u32, vp]
     L.fsr1_shard_status.argtypes = [vp]
+    L.fsr1_shard_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), u32, u32p]
     L.fsr1_error_string.restype = ctypes.c_char_p
     L.fsr1_error_string.argtypes = [ctypes.c_int]
     L.fsr1_last_kernel_name.restype = ctypes.c_char_p

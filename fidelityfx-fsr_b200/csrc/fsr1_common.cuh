@@ -33,6 +33,7 @@ struct HaloSync {
   uint32_t* credit[2];
   uint32_t* counter;  // CTAs finished (device memory, zero between launches)
   uint32_t* status;   // != 0: a wait timed out
+  unsigned long long* trace;  // optional (fsr1_shard_trace): globaltimer at [0] wait begin, [1] wait end (CTA 0), [2] last CTA done
   uint32_t seq;
 };
 
@@ -206,8 +207,11 @@ __device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t want) 
 __device__ __forceinline__ void halo_sync_begin(const HaloSync& hs) {
   if (hs.ready[0] || hs.ready[1]) {
     if (threadIdx.x == 0) {
+      const bool tr = hs.trace && blockIdx.x == 0 && blockIdx.y == 0;
+      if (tr) hs.trace[0] = global_ns();
       if (hs.ready[0] && !spin_until(hs.ready[0], hs.seq)) atomicExch(hs.status, 3u);
       if (hs.ready[1] && !spin_until(hs.ready[1], hs.seq)) atomicExch(hs.status, 4u);
+      if (tr) hs.trace[1] = global_ns();
     }
     __syncthreads();
   }
@@ -221,6 +225,7 @@ __device__ __forceinline__ void halo_sync_end(const HaloSync& hs) {
       if (atomicAdd(hs.counter, 1u) == gridDim.x * gridDim.y - 1) {
         atomicExch(hs.counter, 0u);
         __threadfence();
+        if (hs.trace) hs.trace[2] = global_ns();
         if (hs.credit[0]) st_release_sys(hs.credit[0], hs.seq);
         if (hs.credit[1]) st_release_sys(hs.credit[1], hs.seq);
       }

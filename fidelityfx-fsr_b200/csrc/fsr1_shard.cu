@@ -41,6 +41,7 @@ constexpr uint32_t kStatusIdx = kMaxSlots * 4;  // != 0: a spin timed out (value
 __host__ __device__ inline uint32_t counter_idx(uint32_t slot) { return kStatusIdx + 1 + slot; }  // CTAs of the slot's EASU that finished
 __host__ __device__ inline uint32_t push_cnt_idx(uint32_t slot, int side) { return kStatusIdx + 1 + kMaxSlots + slot * 2 + side; }  // push parts done
 constexpr int kPushParts = 8;  // one-warp CTAs per direction
+constexpr uint32_t kTraceFrames = 256, kTraceWords = 8;  // fsr1_shard_trace: device timestamps of the last frames
 
 struct PushSide {
   const uint4* src;        // my rows (local)
@@ -49,6 +50,7 @@ struct PushSide {
   const uint32_t* credit;  // local: the neighbour has finished reading the previous use of this slot
   uint32_t* ready;         // peer: "your halo rows for use q are in place"
   uint32_t* parts_done;    // local: one-warp CTAs of this push that have finished
+  unsigned long long* trace;  // optional: [3 + 2 side] first part started copying, [4 + 2 side] published
 };
 
 // kPushParts one-warp CTAs per direction (blockIdx.x / kPushParts = 0: up, 1: down), each moving 1/kPushParts of the rows.  32 threads
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(32) halo_push_kernel(const PushSide up, const 
     if (!ok) atomicExch(status, 1u + side);
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (s.trace && part == 0 && threadIdx.x == 0) s.trace[3 + 2 * side] = fsr1::global_ns();
   if (ok) {
     const uint32_t per = (s.n16 + kPushParts - 1) / kPushParts, first = part * per;
     const uint32_t end = first + per < s.n16 ? first + per : s.n16;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(32) halo_push_kernel(const PushSide up, const 
     atomicExch(s.parts_done, 0u);
     __threadfence_system();  // acquire side of the counter: the other parts' stores (fenced before their increment) precede the flag
     if (ok) st_release_sys(s.ready, q);
+    if (s.trace) s.trace[4 + 2 * side] = fsr1::global_ns();
   }
 }
 
@@ -133,6 +137,8 @@ struct fsr1_shard {
   cudaStream_t s_comm, s_easu, s_rcas;
   cudaEvent_t ev_in[kMaxSlots], ev_push[kMaxSlots], ev_easu[kMaxSlots], ev_rcas[kMaxSlots];
   bool attached;
+  unsigned long long* trace;  // FSR1_SHARD_TRACE: kTraceFrames x kTraceWords globaltimer stamps (device memory), else null
+  unsigned long long frames;  // frames submitted
   bool inkernel_sync;  // the EASU / fused kernel of this configuration carries the hand-shake itself (HaloSync)
 };
 
@@ -231,6 +237,11 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
     fsr1_shard_destroy(s);
     return FSR1_ERR_CUDA;
   }
+  if ((flags & FSR1_SHARD_TRACE) && (cudaMalloc((void**)&s->trace, sizeof(unsigned long long) * kTraceFrames * kTraceWords) != cudaSuccess ||
+                                     cudaMemset(s->trace, 0, sizeof(unsigned long long) * kTraceFrames * kTraceWords) != cudaSuccess)) {
+    fsr1_shard_destroy(s);
+    return FSR1_ERR_CUDA;
+  }
   for (uint32_t i = 0; i < slots; i++) {
     if (cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_push[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -254,7 +265,7 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
     fsr1_shard_window(s, 0, &win);
     fsr1_shard_output(s, 0, &out);
     fsr1_image tmp0 = {s->tmp, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a, s->easu_rows.b - s->easu_rows.a, s->format, 0};
-    const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+    const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE);
     const fsr1::HaloSync none = {};
     fsr1::set_halo_sync(&none);  // does this configuration's kernel take the hand-shake? (null pointers: a no-op inside the kernel)
     int rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, s->s_easu);
@@ -286,6 +297,7 @@ void fsr1_shard_destroy(fsr1_shard* s) {
   if (s->s_easu) cudaStreamDestroy(s->s_easu);
   if (s->s_rcas) cudaStreamDestroy(s->s_rcas);
   cudaFree(s->arena);
+  cudaFree(s->trace);
   cudaFree(s->tmp);
   cudaFree(s->out);
   delete s;
@@ -397,6 +409,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   const bool one_stream = (s->flags & FSR1_SHARD_ONE_STREAM) != 0;
   cudaStream_t se = s->s_easu, sr = one_stream ? s->s_easu : s->s_rcas;
   const uint32_t q = ++s->seq[slot];
+  struct FrameCount { fsr1_shard* s; ~FrameCount() { s->frames++; } } frame_count{s};
   uint32_t* flags = reinterpret_cast<uint32_t*>(s->arena);
   cudaError_t e;
   if ((e = cudaEventRecord(s->ev_in[slot], caller)) != cudaSuccess) return cuda_rc(e);
@@ -405,7 +418,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   if (up || down) {
     PushSide ps[2];
     for (int side = 0; side < 2; side++) {
-      ps[side] = PushSide{nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+      ps[side] = PushSide{nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr};
       const bool has = side == kFromUp ? up : down;
       if (!has) continue;
       const Rows r = s->send[side];
@@ -415,6 +428,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
       ps[side].n16 = (uint32_t)((uint64_t)(r.b - r.a) * s->pitch / 16);
       ps[side].credit = flags + credit_idx(slot, side);
       ps[side].parts_done = flags + push_cnt_idx(slot, side);
+      ps[side].trace = s->trace ? s->trace + (size_t)(s->frames % kTraceFrames) * kTraceWords : nullptr;
       // I am the neighbour's lower (upper) peer when I push up (down)
       ps[side].ready = pf + ready_idx(slot, side == kFromUp ? kFromDown : kFromUp);
     }
@@ -430,7 +444,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   fsr1_shard_output(s, slot, &out);
   fsr1_image tmp = make_img(s->tmp + (uint64_t)slot * s->tmp_slot_stride, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a,
                             s->easu_rows.b - s->easu_rows.a, s->format);
-  const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO);
+  const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE);
   fsr1::HaloSync hs = {};
   hs.ready[kFromUp] = up ? flags + ready_idx(slot, kFromUp) : nullptr;
   hs.ready[kFromDown] = down ? flags + ready_idx(slot, kFromDown) : nullptr;
@@ -438,6 +452,7 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   hs.credit[kFromDown] = down ? reinterpret_cast<uint32_t*>(s->peer[kFromDown]) + credit_idx(slot, kFromUp) : nullptr;
   hs.counter = flags + counter_idx(slot);
   hs.status = flags + kStatusIdx;
+  hs.trace = s->trace ? s->trace + (size_t)(s->frames % kTraceFrames) * kTraceWords : nullptr;
   hs.seq = q;
   const bool shake = up || down, inkernel = shake && s->inkernel_sync;
   const bool fused = (kflags & FSR1_FLAG_FUSED) != 0;
@@ -486,6 +501,24 @@ int fsr1_shard_wait(fsr1_shard* s, uint32_t slot, void* stream) {
   if ((e = cudaStreamWaitEvent(caller, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);
   if (s->world > 1 && !(s->flags & FSR1_SHARD_SKIP_HALO) && (e = cudaStreamWaitEvent(caller, s->ev_push[slot], 0)) != cudaSuccess)
     return cuda_rc(e);  // my rows have left
+  return FSR1_OK;
+}
+
+int fsr1_shard_trace(fsr1_shard* s, uint64_t* out, uint32_t max_frames, uint32_t* n_frames) {
+  if (!s || !out || !n_frames) return FSR1_ERR_INVALID_ARGUMENT;
+  *n_frames = 0;
+  if (!s->trace) return FSR1_OK;
+  DeviceGuard g(s->device);
+  uint32_t n = (uint32_t)(s->frames < kTraceFrames ? s->frames : kTraceFrames);
+  if (n > max_frames) n = max_frames;
+  // oldest first: frames [frames - n, frames)
+  for (uint32_t i = 0; i < n; i++) {
+    const unsigned long long f = s->frames - n + i;
+    if (cudaMemcpy(out + (size_t)i * kTraceWords, s->trace + (size_t)(f % kTraceFrames) * kTraceWords, sizeof(unsigned long long) * kTraceWords,
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      return FSR1_ERR_CUDA;
+  }
+  *n_frames = n;
   return FSR1_OK;
 }
 

@@ -155,6 +155,7 @@ int fsr1_context_upscale_host(fsr1_context* ctx, const void* in_host, uint64_t i
 typedef struct fsr1_shard fsr1_shard;
 #define FSR1_SHARD_HANDLE_BYTES 64
 #define FSR1_SHARD_ONE_STREAM (1u << 16) /* fsr1_shard_create flag: EASU and RCAS of a frame on one stream (no frame overlap) */
+#define FSR1_SHARD_TRACE (1u << 18)      /* keep device timestamps of the last 256 frames (fsr1_shard_trace)                          */
 #define FSR1_SHARD_SKIP_HALO (1u << 17)  /* MEASUREMENT ONLY: no halo exchange (slab borders are wrong); times the frame without it */
 
 typedef struct fsr1_shard_info {   /* logical row ranges [row0, row1) of this rank */
@@ -185,6 +186,9 @@ void* fsr1_shard_arena(const fsr1_shard* shard);
 int fsr1_shard_submit(fsr1_shard* shard, uint32_t slot, void* stream);
 /* Orders `stream` after the slot's result (and after this rank's halo rows have left: the input may be rewritten). */
 int fsr1_shard_wait(fsr1_shard* shard, uint32_t slot, void* stream);
+/* FSR1_SHARD_TRACE: 8 GPU globaltimer stamps (ns) per frame, oldest first: [0] EASU began waiting for its halo, [1] halo present,
+ * [2] last EASU CTA done (credit sent), [3]/[5] push up/down started, [4]/[6] push up/down published, [7] unused. */
+int fsr1_shard_trace(fsr1_shard* shard, uint64_t* out /* max_frames x 8 */, uint32_t max_frames, uint32_t* n_frames);
 int fsr1_shard_status(fsr1_shard* shard);  /* FSR1_OK, or FSR1_ERR_TIMEOUT if a neighbour never answered (call after a sync) */
 
 /* ---- pointwise companions of the scaling path (ffx-fsr/ffx_fsr1.h:986-1199) ----------------------
