@@ -324,19 +324,33 @@ def run_ours(args, rank, world, local_rank):
         def drain():
             stream.wait_stream(comm)
 
+    rendezvous = torch.zeros(1, device=dev) if dist is not None else None
+
     def timed(fn, n, post=None):
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for i in range(n):
-            fn(i)
-        if post:
-            post()
-        b.record(stream)
-        torch.cuda.synchronize()
+        """K steps between a barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
+        N > 1: hosts leave a barrier milliseconds apart (measured: 7-10 ms on this stack), which at 20 steps would be most of the
+        timed region — so the start event sits behind a DEVICE-side rendezvous (a one-element all_reduce enqueued on the same
+        stream): the clock of every rank starts when the last rank's GPU arrives, and every timed step is ordered after it."""
+        import gc
+        gc.collect()
+        gc.disable()                       # no collector pause inside the timed region
+        try:
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if dist is not None:
+                dist.all_reduce(rendezvous)    # async w.r.t. the host; `stream` waits for it
+            a.record(stream)
+            for i in range(n):
+                fn(i)
+            if post:
+                post()
+            b.record(stream)
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         ms = a.elapsed_time(b)
         if dist is not None:
             t = torch.tensor([ms], device=dev)
@@ -349,15 +363,17 @@ def run_ours(args, rank, world, local_rank):
         step(i)
     drain()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("FSR1_BENCH_NO_SAMPLER"):
         sampler.start()
     launches0 = api.launch_count()
     ms = timed(step, K, post=drain)
     launches = api.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = (sampler.stop() if not os.environ.get("FSR1_BENCH_NO_SAMPLER") else sampler._smi_once()) if rank == 0 else None
     up.status()
     if args.trace and world > 1 and halo_mode == "p2p":
         tr = up.trace().astype(np.int64)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "trace_rank%d_%s.npy" % (rank, os.environ.get("FSR1_TRACE_TAG", "t"))), tr)
         if len(tr) > 8:
             tr = tr[4:-2]
             wait = (tr[:, 1] - tr[:, 0]) / 1e3
