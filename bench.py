@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     halo_mode = args.halo if world > 1 else "p2p"
     kflags = api.FLAG_FUSED if args.fused else 0
     up = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo=halo_mode,
-                           one_stream=args.no_pipeline, flags=kflags, trace=args.trace and world > 1)
+                           one_stream=args.no_pipeline, flags=kflags, trace=args.trace and world > 1, alternate=args.alternate)
     plan = up.plan
     o0, o1 = plan.owned_in_rows(rank)
     e0, e1 = plan.easu_rows(rank)
@@ -458,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         parity = check_sharded_parity(F, api, up, dist, dev, rank, world, iw, ih, ow, oh, H_in, H_out, tdt, rank_rows, halo_mode)
         nh = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo="p2p",
-                               one_stream=args.no_pipeline, skip_halo=True, flags=kflags)
+                               one_stream=args.no_pipeline, skip_halo=True, flags=kflags, alternate=args.alternate)
         for t in range(RING):
             nh.input(t).copy_(up.input(t))
 
@@ -655,6 +655,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--fused", action="store_true", help="FSR1_FLAG_FUSED: EASU and RCAS in one kernel (intermediate in shared memory); roofline against bpp*(Pin+Pout)")
+    ap.add_argument("--alternate", action="store_true", help="whole frames on two streams in turn instead of EASU / RCAS on their own streams")
     ap.add_argument("--trace", action="store_true", help="multi-GPU p2p: print device-timestamp statistics of the halo hand-shake per rank (stderr)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo data plane: direct NVLink stores through the C ABI (default) or NCCL send/recv")
     args = ap.parse_args()

@@ -91,10 +91,15 @@ static inline int host_fp(int o, float scale, float offset) {
   return (int)floorf(s);
 }
 
-static inline int sm_count() {  // of the CURRENT device (one process may drive several)
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-    n = 148;
+static inline int sm_count() {  // of the CURRENT device (one process may drive several); queried once per device
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev];
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;  // benign race: every thread writes the same value
+  }
   return n;
 }
 

@@ -265,7 +265,7 @@ int fsr1_shard_create(fsr1_shard** out_sh, uint32_t in_w, uint32_t in_h, uint32_
     fsr1_shard_window(s, 0, &win);
     fsr1_shard_output(s, 0, &out);
     fsr1_image tmp0 = {s->tmp, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a, s->easu_rows.b - s->easu_rows.a, s->format, 0};
-    const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE);
+    const uint32_t kflags = flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE | FSR1_SHARD_ALTERNATE);
     const fsr1::HaloSync none = {};
     fsr1::set_halo_sync(&none);  // does this configuration's kernel take the hand-shake? (null pointers: a no-op inside the kernel)
     int rc = fsr1_upscale(&win, &tmp0, &out, s->econ, s->rcon, s->out_rows.a, s->out_rows.b, kflags, s->s_easu);
@@ -437,14 +437,20 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     if ((e = cudaEventRecord(s->ev_push[slot], s->s_comm)) != cudaSuccess) return cuda_rc(e);
   }
-  if ((e = cudaStreamWaitEvent(se, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
-  if (q > 1 && !one_stream && (e = cudaStreamWaitEvent(se, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);  // the slot's intermediate is free
   fsr1_image win, out;
   fsr1_shard_window(s, slot, &win);
   fsr1_shard_output(s, slot, &out);
   fsr1_image tmp = make_img(s->tmp + (uint64_t)slot * s->tmp_slot_stride, s->out_pitch, s->out_w, s->out_h, s->easu_rows.a,
                             s->easu_rows.b - s->easu_rows.a, s->format);
-  const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE);
+  const uint32_t kflags = s->flags & ~(uint32_t)(FSR1_SHARD_ONE_STREAM | FSR1_SHARD_SKIP_HALO | FSR1_SHARD_TRACE | FSR1_SHARD_ALTERNATE);
+  const bool fused = (kflags & FSR1_FLAG_FUSED) != 0;
+  // Which streams the frame's kernels run on.  "split" (default): EASU of every frame on se, RCAS on sr — RCAS of frame i overlaps
+  // EASU of frame i+1.  "alternate" (the fused kernel, or FSR1_SHARD_ALTERNATE): the whole frame on one stream, consecutive frames on
+  // se and sr in turn — the same overlap with three driver calls fewer per frame.
+  const bool alternate = !one_stream && (fused || (s->flags & FSR1_SHARD_ALTERNATE));
+  cudaStream_t sk = (alternate && (s->frames & 1)) ? sr : se;
+  if ((e = cudaStreamWaitEvent(sk, s->ev_in[slot], 0)) != cudaSuccess) return cuda_rc(e);
+  if (q > 1 && !one_stream && (e = cudaStreamWaitEvent(sk, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);  // the slot's intermediate / output are free
   fsr1::HaloSync hs = {};
   hs.ready[kFromUp] = up ? flags + ready_idx(slot, kFromUp) : nullptr;
   hs.ready[kFromDown] = down ? flags + ready_idx(slot, kFromDown) : nullptr;
@@ -455,14 +461,6 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   hs.trace = s->trace ? s->trace + (size_t)(s->frames % kTraceFrames) * kTraceWords : nullptr;
   hs.seq = q;
   const bool shake = up || down, inkernel = shake && s->inkernel_sync;
-  const bool fused = (kflags & FSR1_FLAG_FUSED) != 0;
-  // fused: one kernel per frame (fsr1_upscale falls back to the two kernels where the fused one does not apply), consecutive frames
-  // alternate between the two streams; two-kernel path: EASU on se, RCAS on sr
-  cudaStream_t sk = (fused && !one_stream && ((q + slot) & 1)) ? sr : se;
-  if (sk != se) {  // the frame's stream starts after the input / intermediate events waited on se
-    if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
-    if ((e = cudaStreamWaitEvent(sk, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
-  }
   if (shake && !inkernel) {
     halo_wait_kernel<<<1, 32, 0, sk>>>(hs.ready[kFromUp], hs.ready[kFromDown], q, flags + kStatusIdx);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
@@ -478,29 +476,17 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
     credit_signal_kernel<<<1, 32, 0, sk>>>(hs.credit[kFromUp], hs.credit[kFromDown], q);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
   }
-  if (fused) {
-    if ((e = cudaEventRecord(s->ev_rcas[slot], sk)) != cudaSuccess) return cuda_rc(e);
-    return FSR1_OK;
+  cudaStream_t s_last = sk;
+  if (!fused) {
+    if (!one_stream && !alternate) {  // split: RCAS on the other stream, behind an event
+      if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
+      if ((e = cudaStreamWaitEvent(sr, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
+      s_last = sr;
+    }
+    rc = fsr1_rcas(&tmp, &out, s->rcon, s->out_rows.a, s->out_rows.b, kflags, s_last);
+    if (rc != FSR1_OK) return rc;
   }
-  if (!one_stream) {
-    if ((e = cudaEventRecord(s->ev_easu[slot], se)) != cudaSuccess) return cuda_rc(e);
-    if ((e = cudaStreamWaitEvent(sr, s->ev_easu[slot], 0)) != cudaSuccess) return cuda_rc(e);
-  }
-  rc = fsr1_rcas(&tmp, &out, s->rcon, s->out_rows.a, s->out_rows.b, kflags, sr);
-  if (rc != FSR1_OK) return rc;
-  if ((e = cudaEventRecord(s->ev_rcas[slot], sr)) != cudaSuccess) return cuda_rc(e);
-  return FSR1_OK;
-}
-
-int fsr1_shard_wait(fsr1_shard* s, uint32_t slot, void* stream) {
-  if (!s || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
-  if (s->seq[slot] == 0) return FSR1_OK;
-  DeviceGuard g(s->device);
-  cudaStream_t caller = static_cast<cudaStream_t>(stream);
-  cudaError_t e;
-  if ((e = cudaStreamWaitEvent(caller, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);
-  if (s->world > 1 && !(s->flags & FSR1_SHARD_SKIP_HALO) && (e = cudaStreamWaitEvent(caller, s->ev_push[slot], 0)) != cudaSuccess)
-    return cuda_rc(e);  // my rows have left
+  if ((e = cudaEventRecord(s->ev_rcas[slot], s_last)) != cudaSuccess) return cuda_rc(e);
   return FSR1_OK;
 }
 
