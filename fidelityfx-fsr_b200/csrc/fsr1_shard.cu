@@ -490,6 +490,18 @@ int fsr1_shard_submit(fsr1_shard* s, uint32_t slot, void* stream) {
   return FSR1_OK;
 }
 
+int fsr1_shard_wait(fsr1_shard* s, uint32_t slot, void* stream) {
+  if (!s || slot >= s->slots) return FSR1_ERR_INVALID_ARGUMENT;
+  if (s->seq[slot] == 0) return FSR1_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = cudaStreamWaitEvent(caller, s->ev_rcas[slot], 0)) != cudaSuccess) return cuda_rc(e);
+  if (s->world > 1 && !(s->flags & FSR1_SHARD_SKIP_HALO) && (e = cudaStreamWaitEvent(caller, s->ev_push[slot], 0)) != cudaSuccess)
+    return cuda_rc(e);  // my rows have left
+  return FSR1_OK;
+}
+
 int fsr1_shard_trace(fsr1_shard* s, uint64_t* out, uint32_t max_frames, uint32_t* n_frames) {
   if (!s || !out || !n_frames) return FSR1_ERR_INVALID_ARGUMENT;
   *n_frames = 0;
