@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     halo_mode = args.halo if world > 1 else "p2p"
     kflags = api.FLAG_FUSED if args.fused else 0
     up = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo=halo_mode,
-                           one_stream=args.no_pipeline, flags=kflags, trace=args.trace and world > 1, alternate=args.alternate)
+                           one_stream=args.no_pipeline, flags=kflags, trace=args.trace and world > 1)
     plan = up.plan
     o0, o1 = plan.owned_in_rows(rank)
     e0, e1 = plan.easu_rows(rank)
@@ -458,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         parity = check_sharded_parity(F, api, up, dist, dev, rank, world, iw, ih, ow, oh, H_in, H_out, tdt, rank_rows, halo_mode)
         nh = F.ShardedUpscaler(iw, H_in, ow, H_out, world, rank, SHARPNESS, dtype=tdt, device=dev, slots=RING, halo="p2p",
-                               one_stream=args.no_pipeline, skip_halo=True, flags=kflags, alternate=args.alternate)
+                               one_stream=args.no_pipeline, skip_halo=True, flags=kflags)
         for t in range(RING):
             nh.input(t).copy_(up.input(t))
 
@@ -542,7 +542,7 @@ def run_ours(args, rank, world, local_rank):
                        "structure": ("ONE fused EASU->RCAS kernel per frame (FSR1_FLAG_FUSED), no intermediate image" if fused_used else
                                      "two kernels per frame through a display-sized fp16 intermediate, as FSR_Filter::Upscale"),
                        "pipelining": "none: one frame at a time on one stream" if args.no_pipeline else
-                                     "RCAS of frame i overlaps EASU of frame i+1 (two streams inside fsr1_shard), same schedule at every N"},
+                                     "whole frames on two streams in turn inside fsr1_shard: RCAS of frame i overlaps EASU of frame i+1; same schedule at every N"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "e2e": e2e,
         }
         if latency_ms is not None:
@@ -655,7 +655,6 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="distinct synthetic frames resident in HBM (default 8; BASELINE configs[2] uses 120)")
     ap.add_argument("--shard-frame", action="store_true", help="multi-GPU: shard the workload's own frame by rows (strong scaling) instead of stacking one frame per rank")
     ap.add_argument("--fused", action="store_true", help="FSR1_FLAG_FUSED: EASU and RCAS in one kernel (intermediate in shared memory); roofline against bpp*(Pin+Pout)")
-    ap.add_argument("--alternate", action="store_true", help="whole frames on two streams in turn instead of EASU / RCAS on their own streams")
     ap.add_argument("--trace", action="store_true", help="multi-GPU p2p: print device-timestamp statistics of the halo hand-shake per rank (stderr)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo data plane: direct NVLink stores through the C ABI (default) or NCCL send/recv")
     args = ap.parse_args()

@@ -162,7 +162,7 @@ class ShardedUpscaler:
     """
 
     def __init__(self, in_w, in_h, out_w, out_h, world, rank, sharpness=0.25, dtype=None, device=None, flags=0, slots=1,
-                 halo=None, one_stream=False, group=None, skip_halo=False, attach=True, trace=False, alternate=False):
+                 halo=None, one_stream=False, group=None, skip_halo=False, attach=True, trace=False):
         import torch
         self.rank, self.world, self.slots = int(rank), int(world), int(slots)
         self.in_w, self.in_h, self.out_w, self.out_h = in_w, in_h, out_w, out_h
@@ -182,13 +182,13 @@ class ShardedUpscaler:
         self._win0 = self.plan.window_rows(rank)[0]
         self._shard = None
         if halo == "p2p":
-            self._init_p2p(sharpness, dtype, one_stream, skip_halo, attach, trace, alternate)
+            self._init_p2p(sharpness, dtype, one_stream, skip_halo, attach, trace)
         else:
             self._init_nccl(dtype)
         self.owned, self.out, self.window = self.inputs[0], self.outputs[0], self.windows[0]
 
     # ------------------------------------------------------------------------------------------ p2p (C ABI) data plane
-    def _init_p2p(self, sharpness, dtype, one_stream, skip_halo=False, attach=True, trace=False, alternate=False):
+    def _init_p2p(self, sharpness, dtype, one_stream, skip_halo=False, attach=True, trace=False):
         import torch
         L = _lib.lib()
         fmt = {torch.float16: _lib.FORMAT_RGBA16F, torch.float32: _lib.FORMAT_RGBA32F, torch.uint8: _lib.FORMAT_RGBA8_UNORM}[dtype]
@@ -196,7 +196,7 @@ class ShardedUpscaler:
         with torch.cuda.device(self.device):
             _lib.check(L.fsr1_shard_create(ctypes.byref(h), self.in_w, self.in_h, self.out_w, self.out_h, fmt, self.world, self.rank,
                                            self.slots, ctypes.c_float(sharpness),
-                                           self.flags | (_lib.SHARD_ONE_STREAM if one_stream else 0) | (_lib.SHARD_SKIP_HALO if skip_halo else 0) | (_lib.SHARD_TRACE if trace else 0) | (_lib.SHARD_ALTERNATE if alternate else 0)))
+                                           self.flags | (_lib.SHARD_ONE_STREAM if one_stream else 0) | (_lib.SHARD_SKIP_HALO if skip_halo else 0) | (_lib.SHARD_TRACE if trace else 0)))
         self._shard = h
         info = _lib.ShardInfo()
         _lib.check(L.fsr1_shard_geometry(h, ctypes.byref(info)))

@@ -154,8 +154,8 @@ int fsr1_context_upscale_host(fsr1_context* ctx, const void* in_host, uint64_t i
  * driving several devices: fsr1_shard_attach_local(shard, shard_of_rank-1, shard_of_rank+1). */
 typedef struct fsr1_shard fsr1_shard;
 #define FSR1_SHARD_HANDLE_BYTES 64
-#define FSR1_SHARD_ONE_STREAM (1u << 16) /* fsr1_shard_create flag: EASU and RCAS of a frame on one stream (no frame overlap) */
-#define FSR1_SHARD_ALTERNATE (1u << 19)  /* whole frames on two streams in turn (instead of EASU on one stream, RCAS on the other)      */
+#define FSR1_SHARD_ONE_STREAM (1u << 16) /* fsr1_shard_create flag: every frame on one stream (no overlap of consecutive frames; default: two
+                                            streams, whole frames in turn, so RCAS of frame i overlaps EASU of frame i+1)                  */
 #define FSR1_SHARD_TRACE (1u << 18)      /* keep device timestamps of the last 256 frames (fsr1_shard_trace)                          */
 #define FSR1_SHARD_SKIP_HALO (1u << 17)  /* MEASUREMENT ONLY: no halo exchange (slab borders are wrong); times the frame without it */
 
