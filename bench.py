@@ -332,8 +332,7 @@ def run_ours(args, rank, world, local_rank):
         timed region — so the start event sits behind a DEVICE-side rendezvous (a one-element all_reduce enqueued on the same
         stream): the clock of every rank starts when the last rank's GPU arrives, and every timed step is ordered after it."""
         import gc
-        gc.collect()
-        gc.disable()                       # no collector pause inside the timed region
+        gc.disable()                       # no collector pause inside the timed region (collected before the warm-up)
         try:
             torch.cuda.synchronize()
             if dist is not None:
@@ -359,10 +358,15 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms
 
+    # everything slow on the host happens BEFORE the warm-up (NVML initialisation is ~80 ms, a full collection tens of ms), so that
+    # the timed steps follow the warm-up steps after a barrier only: the NVLink peer path is still warm (the first push after ~100 ms
+    # of idle measured 120 us instead of 8, profiles/r02_handshake_trace.txt)
+    import gc
+    gc.collect()
+    sampler = ClockSampler(local_rank)
     for i in range(W):
         step(i)
     drain()
-    sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("FSR1_BENCH_NO_SAMPLER"):
         sampler.start()
     launches0 = api.launch_count()

@@ -136,16 +136,17 @@ class PreparedUpscale:
 
 
 class FramePipeline:
-    """A stream of frames over fixed buffer sets, software-pipelined on two CUDA streams: whole frames go to the two streams in
-    turn, so RCAS of frame i (ALU / XU / HBM-bound) overlaps EASU of frame i+1 (FMA-pipe-bound) — ~20 % more throughput than the
-    two kernels of every frame back to back (measured 74.0 vs 89.3 us per 4K frame on B200).  Per-slot events keep a
-    slot's buffers from being reused before its previous frame is done.  The C ABI's fsr1_shard_* does the same in C (and adds row
-    slabs across GPUs); this class shows the schedule with the plain entry points.
+    """A stream of frames over fixed buffer sets, software-pipelined on two CUDA streams with the plain entry points: RCAS of frame
+    i runs on stream B while EASU of frame i+1 runs on stream A.  (The C ABI's fsr1_shard_* runs whole frames on two streams in turn
+    instead — three driver calls fewer per frame, 74.0 vs 76.2 us on B200 — and is what bench.py uses at every GPU count.)  EASU is FMA-pipe-bound and RCAS ALU/XU/issue-bound, and both
+    have ragged tails (persistent CTAs / last wave), so letting them share the SMs raises throughput by ~20 % over
+    running the two kernels of every frame back to back (measured on B200).  Per-slot events keep a
+    slot's intermediate from being overwritten before its RCAS has read it.
 
     sets: list of (inp, tmp, out) images/tensors; econ/rcon: the constant blocks shared by all frames."""
 
     def __init__(self, sets, econ, rcon, flags=0, device=None, priorities=None, easu_rows=(0, 0), rcas_rows=(0, 0)):
-        """priorities: optional CUDA stream priorities of the two streams (lower = more urgent); None = default streams.
+        """priorities: optional (easu, rcas) CUDA stream priorities (lower = more urgent); None = default streams.
         easu_rows / rcas_rows: output row ranges [y0,y1) of the two passes when the images are row-slab windows
         (EASU covers the slab plus the one-row apron RCAS reads); (0, 0) = the whole image."""
         self._erows, self._rrows = tuple(int(v) for v in easu_rows), tuple(int(v) for v in rcas_rows)
@@ -159,8 +160,8 @@ class FramePipeline:
         else:
             self.stream_easu = torch.cuda.Stream(device=device, priority=priorities[0])
             self.stream_rcas = torch.cuda.Stream(device=device, priority=priorities[1])
-        self._done = [None for _ in sets]
-        self._n = 0
+        self._easu_done = [torch.cuda.Event() for _ in sets]
+        self._rcas_done = [None for _ in sets]
 
     def begin(self, stream=None):
         """Order both pipeline streams after `stream` (default: the current stream)."""
@@ -170,20 +171,22 @@ class FramePipeline:
 
     def submit(self, slot):
         a, t, b = self._imgs[slot]
-        s = self.stream_easu if (self._n & 1) == 0 else self.stream_rcas      # whole frames on the two streams in turn
-        self._n += 1
-        if self._done[slot] is not None:
-            s.wait_event(self._done[slot])             # the slot's previous frame (possibly on the other stream) is done
-        h = ctypes.c_void_p(s.cuda_stream)
-        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, self._erows[0], self._erows[1], self._easu_flags, h)
+        sa, sb = self.stream_easu, self.stream_rcas
+        if self._rcas_done[slot] is not None:
+            sa.wait_event(self._rcas_done[slot])       # the slot's intermediate is free again
+        rc = self._L.fsr1_easu(ctypes.byref(a), ctypes.byref(t), self._econ, self._erows[0], self._erows[1], self._easu_flags,
+                               ctypes.c_void_p(sa.cuda_stream))
         if rc:
             _lib.check(rc)
-        rc = self._L.fsr1_rcas(ctypes.byref(t), ctypes.byref(b), self._rcon, self._rrows[0], self._rrows[1], self._flags, h)
+        self._easu_done[slot].record(sa)
+        sb.wait_event(self._easu_done[slot])
+        rc = self._L.fsr1_rcas(ctypes.byref(t), ctypes.byref(b), self._rcon, self._rrows[0], self._rrows[1], self._flags,
+                               ctypes.c_void_p(sb.cuda_stream))
         if rc:
             _lib.check(rc)
-        if self._done[slot] is None:
-            self._done[slot] = torch.cuda.Event()
-        self._done[slot].record(s)
+        if self._rcas_done[slot] is None:
+            self._rcas_done[slot] = torch.cuda.Event()
+        self._rcas_done[slot].record(sb)
 
     def end(self, stream=None):
         """Order `stream` after everything submitted so far."""
