@@ -238,6 +238,32 @@ def cpu_baseline(wl):
     return allc
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """N > 1: keep this rank's host thread (and so its pinned frame buffers: first touch) on the CPUs of the NUMA node its GPU
+    hangs off — the end-to-end leg moves 83 MB per frame per rank through host memory, and eight unplaced ranks share one
+    socket's memory controllers.  Best effort: returns a note for the JSON line, or None when the topology cannot be read."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        text = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return "rank bound to the %d CPUs local to GPU %s" % (len(cpus), bdf)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     global RING
@@ -255,7 +281,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    affinity = None
     if world > 1:
+        affinity = bind_to_gpu_numa_node(local_rank)
         import torch.distributed as dist
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
@@ -552,6 +580,8 @@ def run_ours(args, rank, world, local_rank):
         if latency_ms is not None:
             line["unpipelined_ms_per_step"] = latency_ms
             line["unpipelined_value"] = total_out_px / (latency_ms * 1e-3) / 1e6
+        if affinity:
+            line["config"]["host_affinity"] = affinity
         if parity is not None:
             line["parity"] = parity
         if halo_info is not None:
