@@ -75,12 +75,13 @@ def load_traffic():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread
-    (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as fallback."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML queried from a thread that is armed before the warm-up and
+    released when the timed steps start (the region is 1.5-15 ms, too short for `nvidia-smi -lms`), nvidia-smi as fallback."""
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.t, self.err = index, [], False, None, None
+        self.go = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -101,7 +102,13 @@ class ClockSampler:
         return i
 
     def _poll(self):
+        """First sample 1 ms into the timed region (a 20-step run lasts ~1.6 ms), then one every 5 ms: each sample is two driver
+        queries against the timed GPU, and at N > 1 a hiccup on one rank's GPU is a hiccup of every rank (they run in lockstep
+        through the halo hand-shake), so the region is sampled, not hammered."""
         nv = self.nv
+        self.go.wait()                 # armed before the warm-up, released when the timed region starts (see trigger)
+        time.sleep(0.001)
+        n = 0
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
@@ -109,12 +116,13 @@ class ClockSampler:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0 if n % 4 == 0 else (self.samples[-1][2] if self.samples else 0.0)
                 self.samples.append((sm, reasons, pw))
+                n += 1
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 break
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def start(self):
         if self.nv is None:
@@ -122,11 +130,22 @@ class ClockSampler:
         self.t = threading.Thread(target=self._poll, daemon=True)
         self.t.start()
 
+    def trigger(self):
+        """The timed region starts now (called on the launching thread right before the first timed step)."""
+        self.go.set()
+
     def stop(self):
         if self.nv is None:
             return self._smi_once()
         self.stop_flag = True
+        self.go.set()
         self.t.join(timeout=1)
+        if not self.samples:                       # a region shorter than 1 ms: one sample right behind it
+            try:
+                self.samples.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM),
+                                     self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h), self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:  # noqa: BLE001
+                pass
         sm = sorted(s[0] for s in self.samples)
         reasons = set()
         for _, r, _ in self.samples:
@@ -135,7 +154,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "sm_mhz_min": sm[0] if sm else None,
                 "power_w_max": max((s[2] for s in self.samples), default=None), "samples": len(sm),
-                "reasons": sorted(reasons), "how": "NVML polled every 2 ms during the timed region"}
+                "reasons": sorted(reasons), "how": "NVML sampled 1 ms into the timed region and every 5 ms after"}
 
     def _smi_once(self):
         try:
@@ -354,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
 
     rendezvous = torch.zeros(1, device=dev) if dist is not None else None
 
-    def timed(fn, n, post=None):
+    def timed(fn, n, post=None, on_start=None):
         """K steps between a barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
         N > 1: hosts leave a barrier milliseconds apart (measured: 7-10 ms on this stack), which at 20 steps would be most of the
         timed region — so the start event sits behind a DEVICE-side rendezvous (a one-element all_reduce enqueued on the same
@@ -370,6 +389,8 @@ def run_ours(args, rank, world, local_rank):
             if dist is not None:
                 dist.all_reduce(rendezvous)    # async w.r.t. the host; `stream` waits for it
             a.record(stream)
+            if on_start:
+                on_start()
             for i in range(n):
                 fn(i)
             if post:
@@ -398,7 +419,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not os.environ.get("FSR1_BENCH_NO_SAMPLER"):
         sampler.start()
     launches0 = api.launch_count()
-    ms = timed(step, K, post=drain)
+    ms = timed(step, K, post=drain, on_start=sampler.trigger if rank == 0 else None)
     launches = api.launch_count() - launches0
     clocks = (sampler.stop() if not os.environ.get("FSR1_BENCH_NO_SAMPLER") else sampler._smi_once()) if rank == 0 else None
     up.status()
