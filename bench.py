@@ -275,7 +275,7 @@ def bind_to_gpu_numa_node(local_rank):
                 cpus.add(int(part))
         allowed = os.sched_getaffinity(0)
         cpus &= allowed
-        if cpus and len(cpus) < len(allowed):
+        if len(cpus) >= 8 and len(cpus) < len(allowed):      # never squeeze the rank (NCCL proxy, sampler) onto a few CPUs
             os.sched_setaffinity(0, cpus)
             return "rank bound to the %d CPUs local to GPU %s" % (len(cpus), bdf)
     except Exception:  # noqa: BLE001
