@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfsr1_b200.so")
 FSR1_OK = 0
 FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_RGB10A2_UNORM = 1, 2, 3, 4
 FLAG_RCAS_CLAMP, FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_NO_RCAS, FLAG_H_REFERENCE, FLAG_PRECISE = 1, 2, 4, 8, 16, 32
-FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE, FLAG_FUSED = 64, 128, 256, 512
+FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_OUTPUT_SQUARE, FLAG_FUSED, FLAG_RCAS_HX2 = 64, 128, 256, 512, 1024
 SHARD_ONE_STREAM, SHARD_SKIP_HALO, SHARD_TRACE, SHARD_HANDLE_BYTES = 1 << 16, 1 << 17, 1 << 18, 64
 
 # every symbol include/fsr1_b200.h declares
@@ -17,6 +17,7 @@ SYMBOLS = ["fsr1_easu", "fsr1_rcas", "fsr1_easu_input_rows", "fsr1_upscale", "fs
            "fsr1_context_destroy", "fsr1_context_upscale", "fsr1_context_upscale_render", "fsr1_context_upscale_host", "fsr1_easu_con",
            "fsr1_easu_con_offset", "fsr1_rcas_con", "fsr1_abi_version", "fsr1_error_string",
            "fsr1_last_cuda_error", "fsr1_launch_count", "fsr1_last_kernel_name", "fsr1_srtm", "fsr1_lfga", "fsr1_tepd",
+           "fsr1_srtm_h", "fsr1_lfga_h", "fsr1_tepd_h",
            "fsr1_shard_create", "fsr1_shard_destroy", "fsr1_shard_geometry", "fsr1_shard_export", "fsr1_shard_attach",
            "fsr1_shard_attach_local", "fsr1_shard_input", "fsr1_shard_window", "fsr1_shard_output", "fsr1_shard_arena",
            "fsr1_shard_submit", "fsr1_shard_wait", "fsr1_shard_status", "fsr1_shard_trace"]
@@ -73,6 +74,9 @@ def lib():
     L.fsr1_srtm.argtypes = [imgp, imgp, ctypes.c_int, u32, u32, vp]
     L.fsr1_lfga.argtypes = [imgp, imgp, imgp, f32, u32, u32, vp]
     L.fsr1_tepd.argtypes = [imgp, imgp, imgp, ctypes.c_int, u32, u32, u32, vp]
+    L.fsr1_srtm_h.argtypes = [imgp, imgp, ctypes.c_int, u32, u32, vp]
+    L.fsr1_lfga_h.argtypes = [imgp, imgp, imgp, f32, u32, u32, vp]
+    L.fsr1_tepd_h.argtypes = [imgp, imgp, imgp, ctypes.c_int, u32, u32, u32, vp]
     L.fsr1_shard_create.argtypes = [ctypes.POINTER(vp), u32, u32, u32, u32, u32, u32, u32, u32, f32, u32]
     L.fsr1_shard_destroy.argtypes = [vp]
     L.fsr1_shard_destroy.restype = None

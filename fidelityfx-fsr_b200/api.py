@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import FORMAT_RGB10A2_UNORM, FORMAT_RGBA8_UNORM  # noqa: F401
-from ._lib import FLAG_FUSED, FLAG_OUTPUT_SQUARE  # noqa: F401
+from ._lib import FLAG_FUSED, FLAG_OUTPUT_SQUARE, FLAG_RCAS_HX2  # noqa: F401
 from ._lib import (FLAG_EXACT, FLAG_FORCE_DIRECT, FLAG_H_REFERENCE, FLAG_NO_RCAS, FLAG_PRECISE, FLAG_RCAS_DENOISE, FLAG_RCAS_PASSTHROUGH_ALPHA, FLAG_RCAS_CLAMP, FORMAT_RGBA16F,  # noqa: F401
                    FORMAT_RGBA32F, Fsr1Error, Image)
 
@@ -117,6 +117,28 @@ def tepd(inp, out, bits, frame=0, dither=None, y0=0, y1=0, stream=None):
     d = _as_img(dither) if dither is not None else None
     _lib.check(_lib.lib().fsr1_tepd(ctypes.byref(a), ctypes.byref(d) if d is not None else None, ctypes.byref(b), bits,
                                     frame, y0, y1, _stream(stream)))
+
+
+def srtm_h(inp, out, inverse=False, y0=0, y1=0, stream=None):
+    """FsrSrtmH / FsrSrtmHx2 and the inverses (ffx_fsr1.h:1049-1055): half arithmetic, packed calling convention; RGBA16F."""
+    a, b = _as_img(inp), _as_img(out)
+    _lib.check(_lib.lib().fsr1_srtm_h(ctypes.byref(a), ctypes.byref(b), 1 if inverse else 0, y0, y1, _stream(stream)))
+
+
+def lfga_h(inp, grain, out, amount, y0=0, y1=0, stream=None):
+    """FsrLfgaH / FsrLfgaHx2 (ffx_fsr1.h:1019-1024); `grain` is an RGBA16F tile."""
+    a, g, b = _as_img(inp), _as_img(grain), _as_img(out)
+    _lib.check(_lib.lib().fsr1_lfga_h(ctypes.byref(a), ctypes.byref(g), ctypes.byref(b), ctypes.c_float(amount), y0, y1,
+                                      _stream(stream)))
+
+
+def tepd_h(inp, out, bits, frame=0, dither=None, y0=0, y1=0, stream=None):
+    """FsrTepdC8H / C10H and the Hx2 forms (ffx_fsr1.h:1137-1199); dither None -> FsrTepdDitH / DitHx2(pixel, frame), else the .w
+    channel of the tiled RGBA16F `dither` image."""
+    a, b = _as_img(inp), _as_img(out)
+    d = _as_img(dither) if dither is not None else None
+    _lib.check(_lib.lib().fsr1_tepd_h(ctypes.byref(a), ctypes.byref(d) if d is not None else None, ctypes.byref(b), bits,
+                                      frame, y0, y1, _stream(stream)))
 
 
 class PreparedUpscale:

@@ -83,7 +83,7 @@ float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 // every flag include/fsr1_b200.h defines
 constexpr uint32_t kAllFlags = FSR1_FLAG_RCAS_CLAMP | FSR1_FLAG_EXACT | FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_NO_RCAS |
                                FSR1_FLAG_H_REFERENCE | FSR1_FLAG_PRECISE | FSR1_FLAG_RCAS_DENOISE |
-                               FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE | FSR1_FLAG_FUSED;
+                               FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE | FSR1_FLAG_FUSED | FSR1_FLAG_RCAS_HX2;
 
 bool window_holds(const fsr1_image* im, int first, int last) {  // logical rows [first,last]
   return first >= (int)im->row0 && last < (int)(im->row0 + im->rows);
@@ -117,6 +117,30 @@ int pointwise(int op, const fsr1_image* in, const fsr1_image* aux, const fsr1_im
   cudaError_t e = launch_pointwise(op, vi, (int)in->format, vo, (int)out->format, aux ? &va : nullptr, aux ? (int)aux->format : 0,
                                    amount, frame, (int)y0, (int)y1, static_cast<cudaStream_t>(stream), &name);
   if (e == cudaErrorNotSupported) return FSR1_ERR_UNSUPPORTED;
+  if (e != cudaSuccess) return cuda_fail(e);
+  t_last_kernel = name;
+  g_launches.fetch_add(1);
+  return FSR1_OK;
+}
+
+// the half-precision (H / Hx2) forms: RGBA16F everywhere
+int pointwise_h(int op, const fsr1_image* in, const fsr1_image* aux, const fsr1_image* out, float amount, uint32_t frame, uint32_t y0,
+                uint32_t y1, void* stream) {
+  int rc;
+  if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
+  if (aux && (rc = check_image(aux)) != FSR1_OK) return rc;
+  if (aux && (aux->row0 != 0 || aux->rows != aux->height)) return FSR1_ERR_INVALID_ARGUMENT;  // tiles are whole images
+  if (in->width != out->width || in->height != out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (in->format != FSR1_FORMAT_RGBA16F || out->format != FSR1_FORMAT_RGBA16F || (aux && aux->format != FSR1_FORMAT_RGBA16F))
+    return FSR1_ERR_UNSUPPORTED;
+  if (y1 == 0) y1 = out->height;
+  if (y0 >= y1 || y1 > out->height) return FSR1_ERR_INVALID_ARGUMENT;
+  if (!window_holds(out, (int)y0, (int)y1 - 1) || !window_holds(in, (int)y0, (int)y1 - 1)) return FSR1_ERR_WINDOW;
+  const ImgView vi = view_of(in), vo = view_of(out);
+  ImgView va;
+  if (aux) va = view_of(aux);
+  const char* name = "";
+  cudaError_t e = launch_pointwise_hx2(op, vi, vo, aux ? &va : nullptr, amount, frame, (int)y0, (int)y1, static_cast<cudaStream_t>(stream), &name);
   if (e != cudaSuccess) return cuda_fail(e);
   t_last_kernel = name;
   g_launches.fetch_add(1);
@@ -248,7 +272,10 @@ int fsr1_rcas(const fsr1_image* in, const fsr1_image* out, const uint32_t con[4]
   const char* name = "";
   bool squared = false;  // the Sample.x hook folded into the kernel's store (c *= c before the one rounding)
   const int fused_square = (flags & FSR1_FLAG_OUTPUT_SQUARE) ? 4 : 0;
-  if (flags & FSR1_FLAG_H_REFERENCE) {
+  if (flags & FSR1_FLAG_RCAS_HX2) {  // the packed calling convention: FsrRcasHx2 + FsrRcasDepackHx2
+    if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
+    e = launch_rcas_hx2(p, s, &name);
+  } else if (flags & FSR1_FLAG_H_REFERENCE) {
     if (in->format != FSR1_FORMAT_RGBA16F || exact) return FSR1_ERR_UNSUPPORTED;
     e = launch_rcas_href(p, s, &name);
   } else if (in->format == FSR1_FORMAT_RGBA16F && !exact && !(flags & FSR1_FLAG_FORCE_DIRECT)) {
@@ -284,7 +311,7 @@ int fsr1_upscale(const fsr1_image* in, const fsr1_image* tmp, const fsr1_image* 
   const uint32_t e0 = y0 == 0 ? 0 : y0 - 1, e1 = y1 >= out->height ? out->height : y1 + 1;
   if ((flags & FSR1_FLAG_FUSED) && in && easu_con && rcas_con && in->format == FSR1_FORMAT_RGBA16F && out->format == FSR1_FORMAT_RGBA16F &&
       !(flags & (FSR1_FLAG_EXACT | FSR1_FLAG_FORCE_DIRECT | FSR1_FLAG_H_REFERENCE | FSR1_FLAG_PRECISE | FSR1_FLAG_RCAS_CLAMP |
-                 FSR1_FLAG_RCAS_DENOISE | FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE))) {
+                 FSR1_FLAG_RCAS_DENOISE | FSR1_FLAG_RCAS_PASSTHROUGH_ALPHA | FSR1_FLAG_OUTPUT_SQUARE | FSR1_FLAG_RCAS_HX2))) {
     int rc;
     if ((rc = check_image(in)) != FSR1_OK || (rc = check_image(out)) != FSR1_OK) return rc;
     if (flags & ~kAllFlags) return FSR1_ERR_INVALID_ARGUMENT;
@@ -332,6 +359,22 @@ int fsr1_tepd(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* 
               uint32_t y0, uint32_t y1, void* stream) {
   if (bits != 8 && bits != 10) return FSR1_ERR_INVALID_ARGUMENT;
   return pointwise(bits == 8 ? 4 : 5, in, dither, out, 0.0f, frame, y0, y1, stream);
+}
+
+int fsr1_srtm_h(const fsr1_image* in, const fsr1_image* out, int inverse, uint32_t y0, uint32_t y1, void* stream) {
+  return pointwise_h(inverse ? 2 : 1, in, nullptr, out, 0.0f, 0u, y0, y1, stream);
+}
+
+int fsr1_lfga_h(const fsr1_image* in, const fsr1_image* grain, const fsr1_image* out, float amount, uint32_t y0, uint32_t y1,
+                void* stream) {
+  if (!grain) return FSR1_ERR_INVALID_ARGUMENT;
+  return pointwise_h(3, in, grain, out, amount, 0u, y0, y1, stream);
+}
+
+int fsr1_tepd_h(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* out, int bits, uint32_t frame, uint32_t y0,
+                uint32_t y1, void* stream) {
+  if (bits != 8 && bits != 10) return FSR1_ERR_INVALID_ARGUMENT;
+  return pointwise_h(bits == 8 ? 4 : 5, in, dither, out, 0.0f, frame, y0, y1, stream);
 }
 
 // ---- context --------------------------------------------------------------------------------------

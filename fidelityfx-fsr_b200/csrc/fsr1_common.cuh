@@ -260,6 +260,10 @@ cudaError_t launch_rcas_f32_packed(const RcasParams& p, cudaStream_t s, const ch
 // Literal FsrEasuH / FsrRcasH semantics, bit-identical to the reference's packed-half source (parity path).
 cudaError_t launch_easu_href(const EasuParams& p, cudaStream_t s, const char** name);
 cudaError_t launch_rcas_href(const RcasParams& p, cudaStream_t s, const char** name);
+// The packed Hx2 calling convention (fsr1_hx2.cu): two pixels per lane in half2 SoA registers, bit-identical to the H source.
+cudaError_t launch_rcas_hx2(const RcasParams& p, cudaStream_t s, const char** name);
+cudaError_t launch_pointwise_hx2(int op, const ImgView& in, const ImgView& out, const ImgView* aux, float amount, uint32_t frame, int y0,
+                                 int y1, cudaStream_t s, const char** name);
 
 // Pointwise companions (fsr1_pointwise.cu): op 1 SRTM, 2 SRTM inverse, 3 LFGA, 4 TEPD 8 bit, 5 TEPD 10 bit, 6 square.
 cudaError_t launch_pointwise(int op, const ImgView& in, int in_format, const ImgView& out, int out_format, const ImgView* aux,

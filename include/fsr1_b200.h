@@ -78,6 +78,11 @@ enum {
                                        RCAS taps read 0, no RCAS options): the intermediate stays in shared memory, `tmp` is not
                                        touched, HBM traffic drops from 26 to 10 bytes per output pixel; results are bit-identical
                                        to the two-kernel path.  Falls back to the two kernels otherwise. */
+  FSR1_FLAG_RCAS_HX2 = 1u << 10,    /* fsr1_rcas, fp16 images only: the reference's PACKED calling convention FsrRcasHx2 +
+                                       FsrRcasDepackHx2 (ffx_fsr1.h:880-984): each lane sharpens pixels ip and ip + (8,0) held as
+                                       half2 structure-of-arrays registers, every operation a packed half operation with its own
+                                       rounding.  Bit-identical to FSR1_FLAG_H_REFERENCE (the reference's Hx2 and H sources agree
+                                       bit for bit); honours RCAS_CLAMP, RCAS_DENOISE, RCAS_PASSTHROUGH_ALPHA.  A parity path. */
   FSR1_FLAG_H_REFERENCE = 1u << 4   /* fp16 images only: the literal FsrEasuH / FsrRcasH arithmetic (packed-half
                                        algorithm, half magic numbers, per-operation half rounding), bit-identical
                                        to the reference's H source; a parity path, slower and LESS accurate than
@@ -209,6 +214,19 @@ int fsr1_lfga(const fsr1_image* in, const fsr1_image* grain, const fsr1_image* o
               uint32_t y1, void* stream);
 int fsr1_tepd(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* out, int bits, uint32_t frame,
               uint32_t y0, uint32_t y1, void* stream);
+
+/* The same passes in the reference's HALF arithmetic, through its packed calling convention (two pixels, p and p + (8,0), per lane
+ * in half2 registers): RGBA16F images only (in, out, grain, dither), every operation rounded to half once, results bit-identical
+ * to the reference's H and Hx2 functions (which agree with each other bit for bit).  Same arguments and rules as above.
+ *   fsr1_srtm_h   FsrSrtmH / FsrSrtmHx2 (inverse == 0), FsrSrtmInvH / FsrSrtmInvHx2     ffx_fsr1.h:1049-1055
+ *   fsr1_lfga_h   FsrLfgaH / FsrLfgaHx2; `amount` is converted to half once               ffx_fsr1.h:1019-1024
+ *   fsr1_tepd_h   FsrTepdC8H / C8Hx2 (bits == 8), FsrTepdC10H / C10Hx2 (bits == 10)      ffx_fsr1.h:1137-1153,1166-1199
+ *                 dither == NULL: FsrTepdDitH / FsrTepdDitHx2(pixel, frame) (:1129-1135,1156-1164); `out` is RGBA16F */
+int fsr1_srtm_h(const fsr1_image* in, const fsr1_image* out, int inverse, uint32_t y0, uint32_t y1, void* stream);
+int fsr1_lfga_h(const fsr1_image* in, const fsr1_image* grain, const fsr1_image* out, float amount, uint32_t y0,
+                uint32_t y1, void* stream);
+int fsr1_tepd_h(const fsr1_image* in, const fsr1_image* dither, const fsr1_image* out, int bits, uint32_t frame,
+                uint32_t y0, uint32_t y1, void* stream);
 
 /* ---- constants through the ABI (for FFIs that cannot include fsr1_host.h) ---------------------- */
 void fsr1_easu_con(uint32_t con[16], float in_viewport_w, float in_viewport_h, float in_size_w, float in_size_h,

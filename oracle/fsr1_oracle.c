@@ -451,3 +451,70 @@ void fsr1o_tepd_f32(const float* in, size_t inPitch, const float* dither, int dw
       o[3] = c[3];
     }
 }
+
+/* ------------------------------------------- pointwise companions, half precision -------------- */
+/* The H entry points (ffx-fsr/ffx_fsr1.h: FsrLfgaH :1019, FsrSrtmH / FsrSrtmInvH :1049-1050, FsrTepdDitH :1129-1135,
+ * FsrTepdC8H / FsrTepdC10H :1137-1153).  The packed Hx2 forms (:1022-1024, :1052-1055, :1156-1199) apply the same
+ * operations to two pixels per lane pair, so they produce these bits too (tests/test_oracle.py checks that on the
+ * reference build).  Images are RGBA16F (raw half bits), pitches in halves; alpha is copied through; every operation
+ * rounds to half (-fexcess-precision=16, no contraction). */
+static inline h16 hmax3(h16 a, h16 b, h16 c) { return hmax(a, hmax(b, c)); }
+
+void fsr1o_lfga_h16(const uint16_t* in, size_t inPitch, const uint16_t* grain, int gw, int gh, size_t gPitch, uint16_t* out,
+                    size_t outPitch, int W, int H, float amount) {
+  const h16 a = (h16)amount, one = (h16)1.0;
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const uint16_t* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      const uint16_t* t = grain + (size_t)(y % gh) * gPitch + (size_t)(x % gw) * 4;
+      uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      for (int k = 0; k < 3; k++) {
+        const h16 v = w2h(c[k]);
+        o[k] = h2w(v + (w2h(t[k]) * a) * hmin(one - v, v));
+      }
+      o[3] = c[3];
+    }
+}
+
+void fsr1o_srtm_h16(const uint16_t* in, size_t inPitch, uint16_t* out, size_t outPitch, int W, int H, int inverse) {
+  const h16 one = (h16)1.0, tiny = (h16)(1.0 / 32768.0);
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const uint16_t* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      const h16 m = hmax3(w2h(c[0]), w2h(c[1]), w2h(c[2]));
+      const h16 r = inverse ? hrcp(hmax(tiny, one - m)) : hrcp(m + one);
+      for (int k = 0; k < 3; k++) o[k] = h2w(w2h(c[k]) * r);
+      o[3] = c[3];
+    }
+}
+
+/* the position hash is computed in fp32 (only 32-bit has the precision) and converted once */
+uint16_t fsr1o_tepd_dit_h16(uint32_t px, uint32_t py, uint32_t frame) { return h2w((h16)fsr1o_tepd_dit(px, py, frame)); }
+
+void fsr1o_tepd_h16(const uint16_t* in, size_t inPitch, const uint16_t* dither, int dw, int dh, size_t dPitch, uint16_t* out,
+                    size_t outPitch, int W, int H, int bits, uint32_t frame) {
+  const h16 q = bits == 8 ? (h16)255.0 : (h16)1023.0, rq = bits == 8 ? (h16)(1.0 / 255.0) : (h16)(1.0 / 1023.0);
+  const h16 inf = w2h(0x7c00u);
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const uint16_t* c = in + (size_t)y * inPitch + (size_t)x * 4;
+      uint16_t* o = out + (size_t)y * outPitch + (size_t)x * 4;
+      const h16 dit = dither ? hsat(w2h(dither[(size_t)(y % dh) * dPitch + (size_t)(x % dw) * 4 + 3]))
+                             : w2h(fsr1o_tepd_dit_h16((uint32_t)x, (uint32_t)y, frame));
+      for (int k = 0; k < 3; k++) {
+        const h16 v = w2h(c[k]);
+        h16 n = (h16)sqrtf((float)v);
+        n = (h16)floorf((float)(n * q)) * rq;
+        const h16 a = n * n;
+        h16 b = n + rq;
+        b = b * b;
+        const h16 r = (v - b) * hprx_med_rcp(a - b);
+        o[k] = h2w(hsat(n + hsat((dit - r) * inf) * rq));
+      }
+      o[3] = c[3];
+    }
+}

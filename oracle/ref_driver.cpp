@@ -226,9 +226,8 @@ void REF_NAME(fsr1ref_rcas_h)(const uint16_t* in, int W, int H, size_t inPitch, 
     }
   }
 }
-#ifdef REF_BASE
 // FsrRcasHx2 (ffx-fsr/ffx_fsr1.h:888-984): lane i of a 16x1 strip produces pixels x0+i and x0+i+8.
-void fsr1ref_rcas_hx2(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
+void REF_NAME(fsr1ref_rcas_hx2)(const uint16_t* in, int W, int H, size_t inPitch, uint16_t* out, size_t outPitch,
                       const uint32_t* con, int oob_clamp, int y0, int y1) {
   AU4 c(con[0], con[1], con[2], con[3]);
 #pragma omp parallel for schedule(dynamic, 4)
@@ -236,19 +235,92 @@ void fsr1ref_rcas_hx2(const uint16_t* in, int W, int H, size_t inPitch, uint16_t
     g_h = ImgH{in, W, H, inPitch}; g_rcas_clamp = oob_clamp;
     for (int x0 = 0; x0 < W; x0 += 16)
       for (int i = 0; i < 8; i++) {
-        AH2 pR, pG, pB;
+        AH2 pR, pG, pB, pA((AH1)1.0, (AH1)1.0);
+#ifdef FSR_RCAS_PASSTHROUGH_ALPHA
+        FsrRcasHx2(pR, pG, pB, pA, AU2((uint)(x0 + i), (uint)y), c);
+#else
         FsrRcasHx2(pR, pG, pB, AU2((uint)(x0 + i), (uint)y), c);
+#endif
         AH4 q0, q1;
         FsrRcasDepackHx2(q0, q1, pR, pG, pB);
         if (x0 + i < W) {
           uint16_t* o = out + (size_t)y * outPitch + (size_t)(x0 + i) * 4;
-          o[0] = h_to_bits(q0.r); o[1] = h_to_bits(q0.g); o[2] = h_to_bits(q0.b); o[3] = 0x3c00;
+          o[0] = h_to_bits(q0.r); o[1] = h_to_bits(q0.g); o[2] = h_to_bits(q0.b); o[3] = h_to_bits(pA.x);
         }
         if (x0 + i + 8 < W) {
           uint16_t* o = out + (size_t)y * outPitch + (size_t)(x0 + i + 8) * 4;
-          o[0] = h_to_bits(q1.r); o[1] = h_to_bits(q1.g); o[2] = h_to_bits(q1.b); o[3] = 0x3c00;
+          o[0] = h_to_bits(q1.r); o[1] = h_to_bits(q1.g); o[2] = h_to_bits(q1.b); o[3] = h_to_bits(pA.y);
         }
       }
+  }
+}
+#ifdef REF_BASE
+// ---- the pointwise companions in half precision: the scalar H functions and the packed Hx2 calling convention --------
+//   FsrLfgaH / FsrLfgaHx2 ffx-fsr/ffx_fsr1.h:1019-1024   FsrSrtmH / InvH / Hx2 / InvHx2 :1049-1056
+//   FsrTepdDitH :1129-1135   FsrTepdC8H / C10H :1137-1153   FsrTepdDitHx2 :1156-1164   FsrTepdC8Hx2 / C10Hx2 :1166-1199
+// Pixels are n interleaved RGBA16F quadruples (raw half bits); alpha is not touched.  The Hx2 entry points pack pixels
+// (2k, 2k+1) into the two lanes (n odd: the last pixel is paired with itself).
+static inline AH3 h3_at(const uint16_t* c, size_t i) { return AH3(h_from_bits(c[4 * i]), h_from_bits(c[4 * i + 1]), h_from_bits(c[4 * i + 2])); }
+static inline void h3_to(uint16_t* c, size_t i, AH3 v) { c[4 * i] = h_to_bits(v.r); c[4 * i + 1] = h_to_bits(v.g); c[4 * i + 2] = h_to_bits(v.b); }
+struct PairH { AH2 r, g, b; };
+static inline PairH pair_at(const uint16_t* c, size_t i, size_t j) {
+  return PairH{AH2(h_from_bits(c[4 * i]), h_from_bits(c[4 * j])), AH2(h_from_bits(c[4 * i + 1]), h_from_bits(c[4 * j + 1])),
+               AH2(h_from_bits(c[4 * i + 2]), h_from_bits(c[4 * j + 2]))};
+}
+static inline void pair_to(uint16_t* c, size_t i, size_t j, const PairH& v) {
+  c[4 * j] = h_to_bits(v.r.y); c[4 * j + 1] = h_to_bits(v.g.y); c[4 * j + 2] = h_to_bits(v.b.y);
+  c[4 * i] = h_to_bits(v.r.x); c[4 * i + 1] = h_to_bits(v.g.x); c[4 * i + 2] = h_to_bits(v.b.x);
+}
+void fsr1ref_lfga_h(uint16_t* c, const uint16_t* t, size_t n, float amount) {
+  for (size_t i = 0; i < n; i++) { AH3 v = h3_at(c, i); FsrLfgaH(v, h3_at(t, i), (AH1)amount); h3_to(c, i, v); }
+}
+void fsr1ref_lfga_hx2(uint16_t* c, const uint16_t* t, size_t n, float amount) {
+  for (size_t i = 0; i < n; i += 2) {
+    const size_t j = i + 1 < n ? i + 1 : i;
+    PairH v = pair_at(c, i, j), g = pair_at(t, i, j);
+    FsrLfgaHx2(v.r, v.g, v.b, g.r, g.g, g.b, (AH1)amount);
+    pair_to(c, i, j, v);
+  }
+}
+void fsr1ref_srtm_h(uint16_t* c, size_t n, int inverse) {
+  for (size_t i = 0; i < n; i++) { AH3 v = h3_at(c, i); if (inverse) FsrSrtmInvH(v); else FsrSrtmH(v); h3_to(c, i, v); }
+}
+void fsr1ref_srtm_hx2(uint16_t* c, size_t n, int inverse) {
+  for (size_t i = 0; i < n; i += 2) {
+    const size_t j = i + 1 < n ? i + 1 : i;
+    PairH v = pair_at(c, i, j);
+    if (inverse) FsrSrtmInvHx2(v.r, v.g, v.b); else FsrSrtmHx2(v.r, v.g, v.b);
+    pair_to(c, i, j, v);
+  }
+}
+void fsr1ref_tepd_dit_h(uint16_t* dit, int w, int h, uint32_t frame) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) dit[(size_t)y * w + x] = h_to_bits(FsrTepdDitH(AU2((uint)x, (uint)y), (AU1)frame));
+}
+// FsrTepdDitHx2 produces the values of positions p and p+(8,0): columns [16k, 16k+8) are lane x, [16k+8, 16k+16) lane y
+void fsr1ref_tepd_dit_hx2(uint16_t* dit, int w, int h, uint32_t frame) {
+  for (int y = 0; y < h; y++)
+    for (int x0 = 0; x0 < w; x0 += 16)
+      for (int i = 0; i < 8; i++) {
+        const AH2 d = FsrTepdDitHx2(AU2((uint)(x0 + i), (uint)y), (AU1)frame);
+        if (x0 + i < w) dit[(size_t)y * w + x0 + i] = h_to_bits(d.x);
+        if (x0 + i + 8 < w) dit[(size_t)y * w + x0 + i + 8] = h_to_bits(d.y);
+      }
+}
+void fsr1ref_tepd_h(uint16_t* c, const uint16_t* dit, size_t n, int bits) {
+  for (size_t i = 0; i < n; i++) {
+    AH3 v = h3_at(c, i);
+    if (bits == 8) FsrTepdC8H(v, h_from_bits(dit[i])); else FsrTepdC10H(v, h_from_bits(dit[i]));
+    h3_to(c, i, v);
+  }
+}
+void fsr1ref_tepd_hx2(uint16_t* c, const uint16_t* dit, size_t n, int bits) {
+  for (size_t i = 0; i < n; i += 2) {
+    const size_t j = i + 1 < n ? i + 1 : i;
+    PairH v = pair_at(c, i, j);
+    const AH2 d(h_from_bits(dit[i]), h_from_bits(dit[j]));
+    if (bits == 8) FsrTepdC8Hx2(v.r, v.g, v.b, d); else FsrTepdC10Hx2(v.r, v.g, v.b, d);
+    pair_to(c, i, j, v);
   }
 }
 int fsr1ref_has_half(void) { return 1; }

@@ -30,6 +30,7 @@ unsigned char* fsr1_emu_dynamic_smem() { return g_dynamic_smem; }
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_rcas_f32.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_fused.cu"
 #include "../../fidelityfx-fsr_b200/csrc/fsr1_easu_f32.cu"
+#include "../../fidelityfx-fsr_b200/csrc/fsr1_hx2.cu"
 
 using namespace fsr1;
 
@@ -336,4 +337,49 @@ extern "C" int emu_easu_f32_pairs(int half_storage, const void* in, int iw, int 
                                   long long out_pitch, const uint32_t* con, int y0, int y1, int max_ctas) {
   return half_storage ? run_f32_pairs<__half>(in, iw, ih, in_pitch, out, ow, oh, out_pitch, con, y0, y1, max_ctas)
                       : run_f32_pairs<float>(in, iw, ih, in_pitch, out, ow, oh, out_pitch, con, y0, y1, max_ctas);
+}
+
+// ---- the packed Hx2 calling convention (csrc/fsr1_hx2.cu): RCAS and the pointwise companions, RGBA16F ------------------------
+template <typename Body> static void run_hx2_grid(int w, int rows, Body body) {
+  const int gx = (w + kHx2Span - 1) / kHx2Span;
+  for (int by = 0; by < rows; by++)
+    for (int bx = 0; bx < gx; bx++) {
+      std::vector<std::thread> ts;
+      for (int t = 0; t < kHx2Threads; t++)
+        ts.emplace_back([=]() {
+          threadIdx = uint3{(unsigned)t, 0, 0};
+          blockIdx = uint3{(unsigned)bx, (unsigned)by, 0};
+          gridDim.x = (unsigned)gx; gridDim.y = (unsigned)rows;
+          blockDim.x = (unsigned)kHx2Threads;
+          body();
+        });
+      for (auto& th : ts) th.join();
+    }
+}
+
+// `in` points at logical row in_row0 and holds in_rows rows (a row-slab window); opts: bit 0 DENOISE, bit 1 PASSTHROUGH_ALPHA
+extern "C" int emu_rcas_hx2(const void* in, int in_row0, int in_rows, void* out, int w, int h, long long in_pitch, long long out_pitch,
+                            const uint32_t* con, int clamp, int y0, int y1, int opts) {
+  RcasParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, in_row0, in_rows};
+  p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
+  memcpy(&p.sharp, &con[0], 4);
+  p.sharp_h2 = con[1];
+  p.y0 = y0; p.y1 = y1; p.clamp = clamp; p.options = opts & 3;
+  run_hx2_grid(w, y1 - y0, [&p]() { rcas_hx2_kernel(p); });
+  return 0;
+}
+
+// op: 1 SRTM, 2 SRTM inverse, 3 LFGA, 4 TEPD 8 bit, 5 TEPD 10 bit; aux = grain / dither tile (aw x ah) or null
+extern "C" int emu_pointwise_hx2(int op, const void* in, long long in_pitch, void* out, long long out_pitch, int w, int h, const void* aux,
+                                 int aw, int ah, long long aux_pitch, float amount, uint32_t frame, int y0, int y1) {
+  if (op < 1 || op > 5 || (op == 3 && !aux)) return -1;
+  PointHParams p;
+  p.in = ImgView{(unsigned char*)in, in_pitch, w, h, 0, h};
+  p.out = ImgView{(unsigned char*)out, out_pitch, w, h, 0, h};
+  p.has_aux = aux ? 1 : 0;
+  p.aux = aux ? ImgView{(unsigned char*)aux, aux_pitch, aw, ah, 0, ah} : p.in;
+  p.op = op; p.amount = amount; p.frame = frame; p.y0 = y0; p.y1 = y1;
+  run_hx2_grid(w, y1 - y0, [&p]() { pointwise_hx2_kernel(p); });
+  return 0;
 }

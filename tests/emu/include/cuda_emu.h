@@ -55,6 +55,7 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+inline float __fsqrt_rn(float a) { volatile float r = sqrtf(a); return r; }
 inline float __saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }  // NaN -> 0
 template <typename T> inline T __ldg(const T* p) { return *p; }
 
@@ -86,6 +87,10 @@ inline __half2 __hfma2_relu(__half2 a, __half2 b, __half2 c) { __half2 r = mkh2(
 inline __half2 __hmul2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) * h2f(b.x)), d2h((double)h2f(a.y) * h2f(b.y))); }
 inline __half2 __hadd2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) + h2f(b.x)), d2h((double)h2f(a.y) + h2f(b.y))); }
 inline __half2 __hsub2(__half2 a, __half2 b) { return mkh2(d2h((double)h2f(a.x) - h2f(b.x)), d2h((double)h2f(a.y) - h2f(b.y))); }
+// the .rn forms that forbid contraction: one IEEE rounding per lane, as above
+inline __half2 __hadd2_rn(__half2 a, __half2 b) { return __hadd2(a, b); }
+inline __half2 __hsub2_rn(__half2 a, __half2 b) { return __hsub2(a, b); }
+inline __half2 __hmul2_rn(__half2 a, __half2 b) { return __hmul2(a, b); }
 inline __half2 __hmul2_sat(__half2 a, __half2 b) { return mkh2(f2h(__saturatef((float)((double)h2f(a.x) * h2f(b.x)))), f2h(__saturatef((float)((double)h2f(a.y) * h2f(b.y))))); }
 inline __half2 __hneg2(__half2 a) { a.x.b ^= 0x8000; a.y.b ^= 0x8000; return a; }
 inline __half2 __habs2(__half2 a) { a.x.b &= 0x7fff; a.y.b &= 0x7fff; return a; }

@@ -118,14 +118,15 @@ def rcas(img, con, clamp=False, y0=0, y1=None, lib=None, denoise=False, alpha=Fa
     return out.view(np.float16) if half else out
 
 
-def rcas_hx2(img, con, clamp=False):
+def rcas_hx2(img, con, clamp=False, denoise=False, alpha=False):
     """The reference's packed calling convention FsrRcasHx2 (two pixels per call), reference build only."""
     lib = ref()
     h, w = img.shape[:2]
     src = img.view(np.uint16)
     out = np.zeros((h, w, 4), np.uint16)
-    lib.fsr1ref_rcas_hx2(P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con),
-                         1 if clamp else 0, 0, h)
+    suffix = {(False, False): "", (True, False): "_dn", (False, True): "_pa", (True, True): "_dnpa"}[(denoise, alpha)]
+    getattr(lib, "fsr1ref_rcas_hx2" + suffix)(P(src.ctypes.data), w, h, Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), _arr(con),
+                                              1 if clamp else 0, 0, h)
     return out.view(np.float16)
 
 
@@ -182,3 +183,69 @@ def tepd(img, bits, frame=0, dither=None, lib=None):
         dit = np.ascontiguousarray(np.clip(dither[gy][:, gx][..., 3], 0.0, 1.0).astype(np.float32))
     lib.fsr1ref_tepd_f(P(out.ctypes.data), P(dit.ctypes.data), Z(h * w), bits)
     return out
+
+
+# ---- pointwise companions in half precision: RGBA16F images [H,W,4] (numpy float16) -------------------------------
+# lib=None: the C restatement; lib=ref(): the reference's own FsrLfgaH / FsrSrtmH / FsrTepdC*H, or with hx2=True its packed
+# calling convention (FsrLfgaHx2 / FsrSrtmHx2 / FsrTepdDitHx2 / FsrTepdC*Hx2).
+def _tile16(aux, h, w):
+    gy, gx = np.arange(h) % aux.shape[0], np.arange(w) % aux.shape[1]
+    return np.ascontiguousarray(aux[gy][:, gx])
+
+
+def lfga_h(img, grain, amount, lib=None, hx2=False):
+    h, w = img.shape[:2]
+    src, g = np.ascontiguousarray(img).view(np.uint16), np.ascontiguousarray(grain).view(np.uint16)
+    if lib is None or lib is oracle():
+        out = np.zeros_like(src)
+        oracle().fsr1o_lfga_h16(P(src.ctypes.data), Z(_pitch(src)), P(g.ctypes.data), g.shape[1], g.shape[0], Z(_pitch(g)),
+                                P(out.ctypes.data), Z(_pitch(out)), w, h, F(amount))
+        return out.view(np.float16)
+    out, tiled = src.copy(), _tile16(g, h, w)
+    getattr(lib, "fsr1ref_lfga_hx2" if hx2 else "fsr1ref_lfga_h")(P(out.ctypes.data), P(tiled.ctypes.data), Z(h * w), F(amount))
+    return out.view(np.float16)
+
+
+def srtm_h(img, inverse=False, lib=None, hx2=False):
+    h, w = img.shape[:2]
+    src = np.ascontiguousarray(img).view(np.uint16)
+    if lib is None or lib is oracle():
+        out = np.zeros_like(src)
+        oracle().fsr1o_srtm_h16(P(src.ctypes.data), Z(_pitch(src)), P(out.ctypes.data), Z(_pitch(out)), w, h, 1 if inverse else 0)
+        return out.view(np.float16)
+    out = src.copy()
+    getattr(lib, "fsr1ref_srtm_hx2" if hx2 else "fsr1ref_srtm_h")(P(out.ctypes.data), Z(h * w), 1 if inverse else 0)
+    return out.view(np.float16)
+
+
+def tepd_dit_h(w, h, frame, lib=None, hx2=False):
+    if lib is None or lib is oracle():
+        oracle().fsr1o_tepd_dit_h16.restype = ctypes.c_uint16
+        oracle().fsr1o_tepd_dit_h16.argtypes = [U, U, U]
+        return np.array([[oracle().fsr1o_tepd_dit_h16(x, y, frame) for x in range(w)] for y in range(h)], np.uint16).view(np.float16)
+    out = np.zeros((h, w), np.uint16)
+    getattr(lib, "fsr1ref_tepd_dit_hx2" if hx2 else "fsr1ref_tepd_dit_h")(P(out.ctypes.data), w, h, U(frame))
+    return out.view(np.float16)
+
+
+def tepd_h(img, bits, frame=0, dither=None, lib=None, hx2=False):
+    """dither: None -> FsrTepdDitH(position, frame); else a tiled [h,w,4] float16 image whose .w channel is the dither."""
+    h, w = img.shape[:2]
+    src = np.ascontiguousarray(img).view(np.uint16)
+    if lib is None or lib is oracle():
+        out = np.zeros_like(src)
+        if dither is not None:
+            d16 = np.ascontiguousarray(dither).view(np.uint16)
+            d = (P(d16.ctypes.data), d16.shape[1], d16.shape[0], Z(_pitch(d16)))
+        else:
+            d = (P(0), 0, 0, Z(0))
+        oracle().fsr1o_tepd_h16(P(src.ctypes.data), Z(_pitch(src)), *d, P(out.ctypes.data), Z(_pitch(out)), w, h, bits, U(frame))
+        return out.view(np.float16)
+    out = src.copy()
+    if dither is None:
+        dit = np.ascontiguousarray(tepd_dit_h(w, h, frame, lib=lib, hx2=hx2)).view(np.uint16)
+    else:
+        t = _tile16(np.ascontiguousarray(dither), h, w)[..., 3].astype(np.float32)
+        dit = np.ascontiguousarray(np.clip(t, 0.0, 1.0).astype(np.float16)).view(np.uint16)
+    getattr(lib, "fsr1ref_tepd_hx2" if hx2 else "fsr1ref_tepd_h")(P(out.ctypes.data), P(dit.ctypes.data), Z(h * w), bits)
+    return out.view(np.float16)

@@ -31,6 +31,18 @@ for shape in ((150, 70, 300, 140), (150, 70, 225, 105)):
     t = torch.zeros((oh, ow, 4), dtype=torch.uint8, device="cuda"); o = torch.zeros_like(t)
     api.upscale(a, t, o, api.easu_con(iw, ih, iw, ih, ow, oh), api.rcas_con(0.25)); torch.cuda.synchronize()
     names.add(api.last_kernel())
+# the packed Hx2 calling convention: widths ending inside a strip, both out-of-image rules, options, tiles that wrap
+for (w, h) in ((300, 11), (37, 9), (5, 4)):
+    img = torch.from_numpy(F.to_half(F.structured(w, h, 7))).cuda()
+    out = torch.zeros_like(img)
+    for fl in (0, api.FLAG_RCAS_CLAMP, api.FLAG_RCAS_DENOISE | api.FLAG_RCAS_PASSTHROUGH_ALPHA):
+        api.rcas(img, out, api.rcas_con(0.25), flags=api.FLAG_RCAS_HX2 | fl)
+    names.add(api.last_kernel())
+    grain = torch.from_numpy(F.to_half(F.uniform(12, 5, 3) - 0.5)).cuda()
+    api.srtm_h(img, out); api.srtm_h(out, out, inverse=True); api.lfga_h(img, grain, out, 0.5)
+    api.tepd_h(img, out, 8, frame=3); api.tepd_h(img, out, 10, dither=grain)
+    torch.cuda.synchronize()
+    names.add(api.last_kernel())
 # row-slab windows whose height is not a multiple of the 4 rows an RCAS lane walks (the 8-GPU split of 2160 rows is 270),
 # through the sharded data plane: 3 ranks on this device, halo by direct stores, two frames per slot
 for dt in (torch.float16, torch.float32):
