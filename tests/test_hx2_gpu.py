@@ -71,7 +71,8 @@ def test_rcas_hx2_options_golden_vectors_row_ranges_and_rejections():
     part = gpu_rcas(img, 0.25, api.FLAG_RCAS_HX2, y0=7, y1=15)
     assert np.array_equal(bits(part[7:15]), bits(full[7:15])) and not bits(part[:7]).any() and not bits(part[15:]).any()
     out = torch.zeros((24, 70, 4), dtype=torch.float16, device="cuda")
-    api.rcas(api.image(dev(img[6:16]), height=24, row0=6), out, api.rcas_con(0.25), y0=7, y1=15, flags=api.FLAG_RCAS_HX2)
+    slab = dev(img[6:16])                                              # rows 6..15: what rows 7..14 read
+    api.rcas(api.image(slab, height=24, row0=6), out, api.rcas_con(0.25), y0=7, y1=15, flags=api.FLAG_RCAS_HX2)
     torch.cuda.synchronize()
     assert np.array_equal(bits(out.cpu().numpy()[7:15]), bits(full[7:15]))
     # the Sample.x square still applies (as a separate pass, like the H-reference kernel)
