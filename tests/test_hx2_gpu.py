@@ -92,12 +92,13 @@ def test_pointwise_h_against_the_reference_golden_vectors():
     assert api.last_kernel() == "pointwise_hx2<FsrSrtmHx2>"
     assert np.array_equal(bits(t), GH["srtm"])
     assert np.array_equal(bits(run(lambda a, b: api.srtm_h(a, b, inverse=True), GH["srtm"].view(np.float16))), GH["srtm_inv"])
+    grain_d, noise_d = dev(grain), dev(noise)
     for amount in (0.0, 0.35, 1.0):
-        got = run(lambda a, b: api.lfga_h(a, dev(grain), b, amount), sdr)
+        got = run(lambda a, b: api.lfga_h(a, grain_d, b, amount), sdr)
         assert np.array_equal(bits(got), GH["lfga_%g" % amount])
     for b_ in (8, 10):
         assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, b_, frame=5), sdr)), GH["tepd%d_f5" % b_])
-        assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, b_, dither=dev(noise)), sdr)), GH["tepd%d_noise" % b_])
+        assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, b_, dither=noise_d), sdr)), GH["tepd%d_noise" % b_])
     assert api.last_kernel() == "pointwise_hx2<FsrTepdC10Hx2>"
 
 
@@ -114,15 +115,16 @@ def test_pointwise_h_bit_identical_to_the_half_oracle(size):
     noise32 = F.uniform(8, 8, 3)
     noise32[0, 0, 3], noise32[0, 1, 3] = -0.5, 1.5
     sdr, hdr, grain, noise = F.to_half(sdr32), F.to_half(hdr32), F.to_half(grain32), F.to_half(noise32)
+    grain_d, noise_d = dev(grain), dev(noise)
     t = run(api.srtm_h, hdr)
     assert np.array_equal(bits(t), bits(ol.srtm_h(hdr)))
     assert np.array_equal(bits(run(lambda a, b: api.srtm_h(a, b, inverse=True), t)), bits(ol.srtm_h(t, inverse=True)))
     for amount in (0.0, 0.35, 1.0):
-        assert np.array_equal(bits(run(lambda a, b: api.lfga_h(a, dev(grain), b, amount), sdr)), bits(ol.lfga_h(sdr, grain, amount)))
+        assert np.array_equal(bits(run(lambda a, b: api.lfga_h(a, grain_d, b, amount), sdr)), bits(ol.lfga_h(sdr, grain, amount)))
     for nbits in (8, 10):
         for frame in (0, 9):
             assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, nbits, frame=frame), sdr)), bits(ol.tepd_h(sdr, nbits, frame=frame)))
-        assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, nbits, dither=dev(noise)), sdr)), bits(ol.tepd_h(sdr, nbits, dither=noise)))
+        assert np.array_equal(bits(run(lambda a, b: api.tepd_h(a, b, nbits, dither=noise_d), sdr)), bits(ol.tepd_h(sdr, nbits, dither=noise)))
     # in place, on a row range only: rows outside [y0,y1) keep their content
     if h >= 9:
         d = dev(hdr)
