@@ -371,12 +371,20 @@ def run_ours(args, rank, world, local_rank):
         def drain():
             stream.wait_stream(comm)
 
-    rendezvous = torch.zeros(1, device=dev) if dist is not None else None
+    # N > 1: the device-side rendezvous in front of every timed region (see timed()).  8 MB rather than one element: the all_reduce then
+    # crosses every NVLink link of every GPU a few microseconds before the clock starts.  The device trace of the 20-step 8-GPU run
+    # (profiles/r02_startup_trace_n8_k20.txt) shows the first halo push after the barrier's idle gap taking 118 us on every rank (218 us
+    # where the receiving GPU had not sent anything itself yet) against 8-16 us from the second frame on — links leaving their idle power
+    # state — which is ~280 us of a 1.9 ms timed region; a stream of frames never idles the links, a barrier in front of 20 steps does.
+    rendezvous = torch.zeros(2 * 1024 * 1024, device=dev) if dist is not None else None
+    if dist is not None:
+        dist.all_reduce(rendezvous)            # first use outside any timed region (NCCL sets up its channels for this size once)
+        torch.cuda.synchronize()
 
     def timed(fn, n, post=None, on_start=None):
         """K steps between a barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
         N > 1: hosts leave a barrier milliseconds apart (measured: 7-10 ms on this stack), which at 20 steps would be most of the
-        timed region — so the start event sits behind a DEVICE-side rendezvous (a one-element all_reduce enqueued on the same
+        timed region — so the start event sits behind a DEVICE-side rendezvous (an all_reduce enqueued on the same
         stream): the clock of every rank starts when the last rank's GPU arrives, and every timed step is ordered after it."""
         import gc
         gc.disable()                       # no collector pause inside the timed region (collected before the warm-up)
@@ -387,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if dist is not None:
-                dist.all_reduce(rendezvous)    # async w.r.t. the host; `stream` waits for it
+                dist.all_reduce(rendezvous)    # async w.r.t. the host; `stream` waits for it; also wakes every NVLink link (see above)
             a.record(stream)
             if on_start:
                 on_start()
@@ -603,6 +611,9 @@ def run_ours(args, rank, world, local_rank):
             line["unpipelined_value"] = total_out_px / (latency_ms * 1e-3) / 1e6
         if affinity:
             line["config"]["host_affinity"] = affinity
+        if world > 1:
+            line["config"]["start"] = ("barrier + synchronize on every rank, then an 8 MB all_reduce on the launching stream in front of the start "
+                                       "event: every rank's clock starts when the last GPU arrives, with the NVLink links out of their idle state")
         if parity is not None:
             line["parity"] = parity
         if halo_info is not None:
