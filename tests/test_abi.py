@@ -78,6 +78,21 @@ def test_error_strings_and_validation_without_gpu():
     assert L.fsr1_tepd(ctypes.byref(h_img), None, ctypes.byref(u10_img), 8, 0, 0, 0, None) == -2  # 8-bit codes into RGB10A2
     win = _lib.Image(addr, 64, 8, 64, 10, 4, 1, 0)
     assert L.fsr1_srtm(ctypes.byref(win), ctypes.byref(win), 0, 0, 0, None) == -3            # window lacks rows [0,64)
+    # the half-precision (H / Hx2) forms: RGBA16F everywhere, the same rules otherwise
+    f32_img = _lib.Image(addr, 128, 8, 4, 0, 4, 2, 0)
+    assert L.fsr1_srtm_h(None, ctypes.byref(h_img), 0, 0, 0, None) == -1
+    assert L.fsr1_srtm_h(ctypes.byref(f32_img), ctypes.byref(f32_img), 0, 0, 0, None) == -2   # half images only
+    assert L.fsr1_srtm_h(ctypes.byref(h_img), ctypes.byref(u8_img), 0, 0, 0, None) == -2
+    assert L.fsr1_srtm_h(ctypes.byref(h_img), ctypes.byref(other), 0, 0, 0, None) == -1
+    assert L.fsr1_lfga_h(ctypes.byref(h_img), None, ctypes.byref(h_img), 0.5, 0, 0, None) == -1
+    assert L.fsr1_lfga_h(ctypes.byref(h_img), ctypes.byref(f32_img), ctypes.byref(h_img), 0.5, 0, 0, None) == -2   # the grain tile too
+    assert L.fsr1_tepd_h(ctypes.byref(h_img), None, ctypes.byref(h_img), 9, 0, 0, 0, None) == -1
+    assert L.fsr1_tepd_h(ctypes.byref(h_img), None, ctypes.byref(u8_img), 8, 0, 0, 0, None) == -2   # writes RGBA16F (fsr1_tepd writes code values)
+    assert L.fsr1_srtm_h(ctypes.byref(win), ctypes.byref(win), 0, 0, 0, None) == -3
+    # FSR1_FLAG_RCAS_HX2 (1 << 10): a known flag, half images only
+    rc4 = (ctypes.c_uint32 * 4)()
+    f32_a, f32_b = _lib.Image(addr, 128, 8, 4, 0, 4, 2, 0), _lib.Image(addr + 2048, 128, 8, 4, 0, 4, 2, 0)
+    assert L.fsr1_rcas(ctypes.byref(f32_a), ctypes.byref(f32_b), rc4, 0, 0, 1 << 10, None) == -2
     assert L.fsr1_launch_count() == 0
 
 
